@@ -1,0 +1,121 @@
+"""ctypes front-end of the C oracle (oracle/fps_oracle.c) and loader of the compiled reference.
+
+TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+``--impl reference`` legs may import this module; fpsample_b200 never does (tests/test_layout.py
+greps for it).  Parity pinning: see the header of fps_oracle.c.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liboracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle with gcc (seconds).  Returns the path of the shared object."""
+    src = os.path.join(_HERE, "fps_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+             src, "-o", _LIB, "-lm"])
+    return _LIB
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        build()
+        L = ctypes.CDLL(_LIB)
+        sz, fp, szp = ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p
+        L.oracle_fps_vanilla.argtypes = [fp, sz, sz, sz, szp, sz, szp]
+        L.oracle_kdline_build.argtypes = [fp, sz, sz, sz, szp, szp, fp, szp]
+        L.oracle_kdline_sample.argtypes = [fp, sz, sz, sz, sz, sz, szp, ctypes.c_void_p]
+        L.oracle_kdline_sample_eager.argtypes = [fp, sz, sz, sz, sz, sz, szp]
+        for f in (L.oracle_fps_vanilla, L.oracle_kdline_build, L.oracle_kdline_sample,
+                  L.oracle_kdline_sample_eager):
+            f.restype = ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def _f32(pc):
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    assert pc.ndim == 2
+    return pc
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed with error code {rc}")
+
+
+def fps_vanilla(pc, k, start=0):
+    """Oracle twin of fpsample.fps_sampling (start: int or list of ints)."""
+    pc = _f32(pc)
+    starts = np.atleast_1d(np.asarray(start, dtype=np.uint64)).copy()
+    out = np.empty(k, dtype=np.uint64)
+    rc = _load().oracle_fps_vanilla(pc.ctypes.data, pc.shape[0], pc.shape[1], k, starts.ctypes.data,
+                                    starts.size, out.ctypes.data)
+    _check(rc, "oracle_fps_vanilla")
+    return out
+
+
+def kdline_build(pc, h):
+    """-> (perm[N] uint64, leaf_bounds[n_leaves+1] uint64, leaf_box[n_leaves,2,D] float32)."""
+    pc = _f32(pc)
+    n, d = pc.shape
+    perm = np.empty(n, dtype=np.uint64)
+    cap = min(1 << min(h, 40), n)
+    bounds = np.empty(cap + 1, dtype=np.uint64)
+    box = np.empty((cap, 2, d), dtype=np.float32)
+    nl = ctypes.c_size_t(0)
+    rc = _load().oracle_kdline_build(pc.ctypes.data, n, d, h, perm.ctypes.data, bounds.ctypes.data,
+                                     box.ctypes.data, ctypes.addressof(nl))
+    _check(rc, "oracle_kdline_build")
+    return perm, bounds[: nl.value + 1].copy(), box[: nl.value].copy()
+
+
+def kdline(pc, k, h, start=0, return_stats=False):
+    """Oracle twin of fpsample.bucket_fps_kdline_sampling (lazy bucket form)."""
+    pc = _f32(pc)
+    out = np.empty(k, dtype=np.uint64)
+    stats = np.zeros(5, dtype=np.uint64)
+    rc = _load().oracle_kdline_sample(pc.ctypes.data, pc.shape[0], pc.shape[1], k, start, h,
+                                      out.ctypes.data, stats.ctypes.data)
+    _check(rc, "oracle_kdline_sample")
+    if return_stats:
+        return out, dict(zip(("point_updates", "bucket_tests", "flushes", "deferred", "dropped"),
+                             (int(x) for x in stats)))
+    return out
+
+
+def kdline_eager(pc, k, h, start=0):
+    """Exact FPS over the permuted array, O(N*K)."""
+    pc = _f32(pc)
+    out = np.empty(k, dtype=np.uint64)
+    rc = _load().oracle_kdline_sample_eager(pc.ctypes.data, pc.shape[0], pc.shape[1], k, start, h,
+                                            out.ctypes.data)
+    _check(rc, "oracle_kdline_sample_eager")
+    return out
+
+
+def load_reference():
+    """Import the unmodified compiled reference (oracle/_ref/fpsample_ref) or return None."""
+    ref_dir = os.path.join(_HERE, "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "fpsample_ref")):
+        return None
+    if ref_dir not in sys.path:
+        sys.path.insert(0, ref_dir)
+    try:
+        import fpsample_ref  # type: ignore
+        return fpsample_ref
+    except Exception:  # pragma: no cover - e.g. ABI mismatch on another interpreter
+        return None
