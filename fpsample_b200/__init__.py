@@ -1,0 +1,162 @@
+"""fpsample_b200 -- B200-native farthest point sampling, drop-in for fpsample's FPS hot path.
+
+Same Python surface as the reference front-end (src/fpsample/__init__.py:35-65, 174-206):
+
+    fps_sampling(pc, n_samples, start_idx=None)                      -> uint64[n_samples]
+    bucket_fps_kdline_sampling(pc, n_samples, h, start_idx=None)     -> uint64[n_samples]
+
+plus batched twins over [B, N, D] arrays (new):
+
+    fps_sampling_batch(pcs, n_samples, start_idx=None, devices=None)               -> uint64[B, n_samples]
+    bucket_fps_kdline_sampling_batch(pcs, n_samples, h, start_idx=None, devices=None)
+
+Everything runs on the GPU through the C ABI in include/fps_b200.h; there is no CPU fallback and the
+import fails loudly when the native extension has not been built (python build_native.py).
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+try:
+    from ._fpsample import (  # noqa: F401
+        __version__,
+        _bucket_fps_kdline_sampling,
+        _bucket_fps_kdline_sampling_batch,
+        _device_count,
+        _fps_sampling,
+        _fps_sampling_batch,
+        _kernel_launches,
+        _last_plan,
+    )
+except ImportError as e:  # pragma: no cover - build problem, never a silent fallback
+    raise ImportError(
+        "fpsample_b200: the native CUDA extension is not built (run `python build_native.py`); "
+        "there is no CPU fallback") from e
+
+
+def get_start_idx(n_pts: int, start_idx: Optional[Union[int, List[int]]]) -> Union[int, np.ndarray]:
+    """Reference: src/fpsample/__init__.py:19-32 (random start honours np.random.seed)."""
+    if start_idx is None:
+        start_idx = np.random.randint(low=0, high=n_pts)
+    elif isinstance(start_idx, int):
+        start_idx = start_idx
+    elif isinstance(start_idx, list):
+        start_idx = np.array(start_idx, dtype=np.uint64)
+    else:
+        raise ValueError("start_idx should be None, int or list")
+    return start_idx
+
+
+def fps_sampling(pc: np.ndarray, n_samples: int,
+                 start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
+    """Vanilla FPS (reference: src/fpsample/__init__.py:35-65 -> src/lib.cpp:188-246).
+
+    Args:
+        pc: point cloud of shape (n_pts, D); cast to float32.
+        n_samples: number of samples.
+        start_idx: None (random), int, or list[int] (forced first picks, all present in the result).
+    Returns:
+        uint64 indices of shape (n_samples,).
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pc.ndim == 2
+    n_pts, _ = pc.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    if isinstance(start_idx, int):
+        assert start_idx is None or 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    if isinstance(start_idx, list):
+        assert len(start_idx) <= n_samples, "len(start_idx) should be <= n_samples"
+        for idx in start_idx:
+            assert 0 <= idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    start_idx = get_start_idx(n_pts, start_idx)
+    return _fps_sampling(pc, n_samples, start_idx)
+
+
+def bucket_fps_kdline_sampling(pc: np.ndarray, n_samples: int, h: int,
+                               start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
+    """QuickFPS with a kd-line of height h (reference: src/fpsample/__init__.py:174-206).
+
+    As in the reference, start_idx addresses the POSITION in the array after the kd build permuted it
+    (src/wrapper.hpp:54-55), so out[0] is generally not start_idx.
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pc.ndim == 2
+    n_pts, _ = pc.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    assert h >= 1, "h should be >= 1"
+    assert 2**h <= n_pts, "2**h should be <= n_pts"
+    assert start_idx is None or 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    if isinstance(start_idx, list):
+        assert len(start_idx) <= n_samples, "len(start_idx) should be <= n_samples"
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    start_idx = get_start_idx(n_pts, start_idx)
+    return _bucket_fps_kdline_sampling(pc, n_samples, h, start_idx)
+
+
+def _batch_start(start_idx, b: int, n_pts: int):
+    if start_idx is None or isinstance(start_idx, int):
+        if isinstance(start_idx, int):
+            assert 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+        return start_idx if start_idx is not None else 0
+    arr = np.ascontiguousarray(start_idx, dtype=np.uint64)
+    assert arr.shape == (b,), "start_idx should be None, int or a sequence of B ints"
+    return arr
+
+
+def fps_sampling_batch(pcs: np.ndarray, n_samples: int,
+                       start_idx: Optional[Union[int, Sequence[int]]] = None,
+                       devices: Optional[Sequence[int]] = None) -> np.ndarray:
+    """Vanilla FPS over a batch [B, N, D]; row b equals fps_sampling(pcs[b], n_samples, start_idx[b]).
+
+    start_idx None means 0 for every cloud (a batch is deterministic by default).  The batch is split
+    into contiguous shards over `devices` (default: every visible B200); no inter-GPU traffic.
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pcs.ndim == 3
+    b, n_pts, _ = pcs.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    pcs = np.ascontiguousarray(pcs, dtype=np.float32)
+    return _fps_sampling_batch(pcs, n_samples, _batch_start(start_idx, b, n_pts),
+                               None if devices is None else list(devices))
+
+
+def bucket_fps_kdline_sampling_batch(pcs: np.ndarray, n_samples: int, h: int,
+                                     start_idx: Optional[Union[int, Sequence[int]]] = None,
+                                     devices: Optional[Sequence[int]] = None) -> np.ndarray:
+    """QuickFPS kd-line over a batch [B, N, D]; row b equals bucket_fps_kdline_sampling(pcs[b], ...)."""
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pcs.ndim == 3
+    b, n_pts, _ = pcs.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    assert h >= 1, "h should be >= 1"
+    assert 2**h <= n_pts, "2**h should be <= n_pts"
+    pcs = np.ascontiguousarray(pcs, dtype=np.float32)
+    return _bucket_fps_kdline_sampling_batch(pcs, n_samples, h, _batch_start(start_idx, b, n_pts),
+                                             None if devices is None else list(devices))
+
+
+def _out_of_scope(name):
+    def f(*a, **k):
+        raise NotImplementedError(
+            f"{name} is outside the accelerated hot path of fpsample_b200 (see DESIGN.md, 'out of scope')")
+    f.__name__ = name
+    return f
+
+
+fps_npdu_sampling = _out_of_scope("fps_npdu_sampling")
+fps_npdu_kdtree_sampling = _out_of_scope("fps_npdu_kdtree_sampling")
+bucket_fps_kdtree_sampling = _out_of_scope("bucket_fps_kdtree_sampling")
+
+__all__ = [
+    "__version__",
+    "fps_sampling",
+    "bucket_fps_kdline_sampling",
+    "fps_sampling_batch",
+    "bucket_fps_kdline_sampling_batch",
+    "fps_npdu_sampling",
+    "fps_npdu_kdtree_sampling",
+    "bucket_fps_kdtree_sampling",
+]

@@ -1,0 +1,162 @@
+"""ctypes binding of the C ABI (include/fps_b200.h) -- what a non-pybind host (or a framework holding
+device pointers) would bind.  Used by the parity tests and bench.py; no compute happens in Python.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfps_b200.so")
+
+ALGO_VANILLA, ALGO_KDLINE = 0, 1
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "fps_b200_vanilla": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 3 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "bucket_fps_kdline": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p]),
+    "fps_b200_vanilla_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "fps_b200_kdline_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "fps_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] + [ctypes.c_size_t] * 5),
+    "fps_b200_vanilla_batch_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fps_b200_kdline_batch_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fps_b200_kdline_build_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
+    "fps_b200_device_count": (ctypes.c_int, []),
+    "fps_b200_version": (ctypes.c_char_p, []),
+    "fps_b200_last_error": (ctypes.c_char_p, []),
+    "fps_b200_last_plan": (ctypes.c_char_p, []),
+    "fps_b200_kernel_launches": (ctypes.c_uint64, []),
+    "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
+    "fps_b200_host_free": (None, [ctypes.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libfps_b200.so (fails loudly if it was not built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python build_native.py` (no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class FpsError(RuntimeError):
+    def __init__(self, fn, rc):
+        self.rc = rc
+        super().__init__(f"{fn} failed with error code {rc}: {lib().fps_b200_last_error().decode()}")
+
+
+def _check(fn, rc):
+    if rc != 0:
+        raise FpsError(fn, rc)
+
+
+def last_plan() -> str:
+    return lib().fps_b200_last_plan().decode()
+
+
+def kernel_launches() -> int:
+    return int(lib().fps_b200_kernel_launches())
+
+
+def device_count() -> int:
+    return int(lib().fps_b200_device_count())
+
+
+def _f32(a, ndim):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == ndim
+    return a
+
+
+# ---- host-pointer entries -------------------------------------------------------------------------------
+def vanilla(pc, k, starts=0):
+    pc = _f32(pc, 2)
+    st = np.atleast_1d(np.asarray(starts, dtype=np.uint64)).copy()
+    out = np.empty(k, dtype=np.uint64)
+    _check("fps_b200_vanilla", lib().fps_b200_vanilla(pc.ctypes.data, pc.shape[0], pc.shape[1], k, st.ctypes.data,
+                                                      st.size, out.ctypes.data))
+    return out
+
+
+def kdline(pc, k, h, start=0):
+    pc = _f32(pc, 2)
+    out = np.empty(k, dtype=np.uint64)
+    _check("bucket_fps_kdline", lib().bucket_fps_kdline(pc.ctypes.data, pc.shape[0], pc.shape[1], k, start, h,
+                                                        out.ctypes.data))
+    return out
+
+
+def _starts(start, b):
+    if start is None:
+        return None
+    st = np.ascontiguousarray(np.broadcast_to(np.asarray(start, dtype=np.uint64), (b,)))
+    return st
+
+
+def vanilla_batch(pcs, k, start=None, devices=None):
+    pcs = _f32(pcs, 3)
+    b, n, d = pcs.shape
+    st = _starts(start, b)
+    dv = None if devices is None else np.asarray(devices, dtype=np.int32)
+    out = np.empty((b, k), dtype=np.uint64)
+    _check("fps_b200_vanilla_batch", lib().fps_b200_vanilla_batch(
+        pcs.ctypes.data, b, n, d, k, None if st is None else st.ctypes.data, out.ctypes.data,
+        None if dv is None else dv.ctypes.data, 0 if dv is None else dv.size))
+    return out
+
+
+def kdline_batch(pcs, k, h, start=None, devices=None):
+    pcs = _f32(pcs, 3)
+    b, n, d = pcs.shape
+    st = _starts(start, b)
+    dv = None if devices is None else np.asarray(devices, dtype=np.int32)
+    out = np.empty((b, k), dtype=np.uint64)
+    _check("fps_b200_kdline_batch", lib().fps_b200_kdline_batch(
+        pcs.ctypes.data, b, n, d, k, None if st is None else st.ctypes.data, h, out.ctypes.data,
+        None if dv is None else dv.ctypes.data, 0 if dv is None else dv.size))
+    return out
+
+
+# ---- device-pointer entries (raw integer addresses, e.g. torch.Tensor.data_ptr()) -------------------------
+def workspace_bytes(algo, b, n, d, k, h=0) -> int:
+    return int(lib().fps_b200_workspace_bytes(algo, b, n, d, k, h))
+
+
+def vanilla_batch_dev(d_pts, b, n, d, k, d_start, d_out, d_ws, ws_bytes, stream=0):
+    _check("fps_b200_vanilla_batch_dev", lib().fps_b200_vanilla_batch_dev(
+        d_pts, b, n, d, k, d_start or None, d_out, d_ws or None, ws_bytes, stream or None))
+
+
+def kdline_batch_dev(d_pts, b, n, d, k, d_start, h, d_out, d_ws, ws_bytes, stream=0):
+    _check("fps_b200_kdline_batch_dev", lib().fps_b200_kdline_batch_dev(
+        d_pts, b, n, d, k, d_start or None, h, d_out, d_ws or None, ws_bytes, stream or None))
+
+
+def kdline_build_dev(d_pts, b, n, d, h, d_perm, d_leaf_lo, d_leaf_box, d_ws, ws_bytes, stream=0):
+    _check("fps_b200_kdline_build_dev", lib().fps_b200_kdline_build_dev(
+        d_pts, b, n, d, h, d_perm, d_leaf_lo or None, d_leaf_box or None, d_ws or None, ws_bytes, stream or None))
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory from the library (freed when the array is collected)."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    p = lib().fps_b200_host_alloc(max(nbytes, 1))
+    if not p:
+        raise MemoryError("fps_b200_host_alloc failed")
+    buf = (ctypes.c_byte * max(nbytes, 1)).from_address(p)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    import weakref
+    weakref.finalize(buf, lib().fps_b200_host_free, p)
+    return arr

@@ -1,0 +1,531 @@
+// capi.cu -- the C-ABI layer (include/fps_b200.h): validation, device contexts, host<->device staging,
+// batch sharding over the devices of one box.  No torch / python types; no CPU fallback.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fps_b200.h"
+#include "engine.h"
+
+namespace fps {
+
+static std::atomic<uint64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local char tl_err[512] = "";
+static thread_local char tl_plan[512] = "";
+
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+    va_end(ap);
+}
+static void set_plan(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_plan, sizeof(tl_plan), fmt, ap);
+    va_end(ap);
+}
+
+#define CK(call)                                                                              \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            set_err("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return FPS_ERR_CUDA + (int)e__;                                                   \
+        }                                                                                     \
+    } while (0)
+
+// ---- devices ---------------------------------------------------------------------------------------------
+struct Buf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return FPS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            set_err("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return FPS_ERR_CUDA + (int)e;
+        }
+        cap = want;
+        return FPS_OK;
+    }
+};
+
+struct Lane {  // one in-flight chunk: its own stream and buffers
+    cudaStream_t st = nullptr;
+    Buf in, out, ws, starts;
+};
+
+struct DevCtx {
+    int dev = -1, n_sms = 0;
+    std::mutex mu;
+    Lane lane[2];
+    bool ready = false;
+};
+
+static std::mutex g_mu;
+static std::vector<int> g_devs;       // usable device ordinals
+static std::vector<DevCtx *> g_ctx;   // indexed by ordinal
+static bool g_scanned = false;
+
+static void scan_devices() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_scanned) return;
+    g_scanned = true;
+    int nd = 0;
+    if (cudaGetDeviceCount(&nd) != cudaSuccess) {
+        cudaGetLastError();
+        nd = 0;
+    }
+    g_ctx.assign(nd, nullptr);
+    for (int d = 0; d < nd; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) {
+            g_devs.push_back(d);
+            g_ctx[d] = new DevCtx();
+            g_ctx[d]->dev = d;
+            cudaDeviceGetAttribute(&g_ctx[d]->n_sms, cudaDevAttrMultiProcessorCount, d);
+        }
+    }
+}
+
+static DevCtx *get_ctx(int dev) {
+    scan_devices();
+    if (dev < 0 || dev >= (int)g_ctx.size() || !g_ctx[dev]) return nullptr;
+    return g_ctx[dev];
+}
+
+static int n_sms_current(int *dev_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    DevCtx *cx = get_ctx(dev);
+    if (dev_out) *dev_out = dev;
+    return cx ? cx->n_sms : 0;
+}
+
+// ---- validation shared by every entry ------------------------------------------------------------------------
+static int check_common(const void *pts, size_t B, size_t n, size_t dim, size_t k, const void *out) {
+    if (!pts || !out || B == 0 || n == 0 || dim == 0 || k == 0 || k > n) {
+        set_err("bad argument: need points/out non-null, B,n,dim >= 1 and 1 <= k <= n (B=%zu n=%zu dim=%zu k=%zu)", B, n,
+                dim, k);
+        return FPS_ERR_ARG;
+    }
+    if (n >= 0xfffffff0ull || k >= 0xfffffff0ull || B >= 0xfffffff0ull || dim > 4096 ||
+        n * dim >= 0xfffffff0ull) {
+        set_err("shape too large for 32-bit indexing (n=%zu dim=%zu k=%zu B=%zu)", n, dim, k, B);
+        return FPS_ERR_UNSUPPORTED;
+    }
+    return FPS_OK;
+}
+
+static int check_kdline(size_t n, size_t dim, size_t h) {
+    if (h == 0) {
+        set_err("height must be >= 1");
+        return FPS_ERR_ARG;
+    }
+    // the reference's python front-end asserts 2**h <= n (src/fpsample/__init__.py:197); the slot-indexed
+    // build keeps 2^h bucket slots, so absurd heights are refused instead of allocating 2^h slots
+    if (h > 24 || (((size_t)1 << h) > 2 * n && h > 6)) {
+        set_err("height %zu is not supported for n=%zu (need 2^h <= 2n or h <= 6)", h, n);
+        return FPS_ERR_UNSUPPORTED;
+    }
+    (void)dim;
+    return FPS_OK;
+}
+
+// ---- enqueue on the current device ------------------------------------------------------------------------------
+struct WsLayout {
+    bool cluster;
+    VanillaPlan vp;
+    VanillaGridPlan gp;
+    size_t off_scratch, off_slots, off_counters, total;
+};
+
+static void vanilla_layout(size_t B, size_t n, size_t dim, int n_sms, WsLayout *L) {
+    L->cluster = plan_vanilla_cluster(n, dim, B, n_sms, &L->vp);
+    L->off_scratch = L->off_slots = L->off_counters = 0;
+    L->total = 256;
+    if (!L->cluster) {
+        plan_vanilla_grid(n, dim, B, n_sms, &L->gp);
+        size_t o = 0;
+        L->off_counters = o;
+        o += ((size_t)L->gp.groups * 32 * 4 + 255) & ~(size_t)255;
+        L->off_slots = o;
+        o += ((size_t)L->gp.groups * 2 * L->gp.G * 8 + 255) & ~(size_t)255;
+        L->off_scratch = o;
+        o += (L->gp.scratch_floats * 4 + 255) & ~(size_t)255;
+        L->total = o + 256;
+    }
+}
+
+static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts,
+                           size_t n_starts, u64 *d_out, void *ws, size_t ws_bytes, int n_sms, cudaStream_t st) {
+    WsLayout L;
+    vanilla_layout(B, n, dim, n_sms, &L);
+    if (L.cluster) {
+        VanillaArgs a;
+        a.pts = d_pts;
+        a.starts = d_starts;
+        a.out = d_out;
+        a.n = (u32)n;
+        a.dim = (u32)dim;
+        a.k = (u32)k;
+        a.n_starts = (u32)(d_starts ? n_starts : 0);
+        a.slice = L.vp.slice;
+        set_plan("vanilla_cluster_kernel<DIM=%d,PPT=%d> clouds=%zu cluster=%u slice=%u smem=%zu", L.vp.dimp, L.vp.ppt, B,
+                 L.vp.C, L.vp.slice, L.vp.smem);
+        CK(launch_vanilla_cluster(L.vp, a, (u32)B, st));
+        count_launch();
+        return FPS_OK;
+    }
+    if (!ws || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", L.total, ws_bytes);
+        return FPS_ERR_WORKSPACE;
+    }
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    VanillaGridArgs g;
+    g.pts = d_pts;
+    g.starts = d_starts;
+    g.out = d_out;
+    g.counters = reinterpret_cast<u32 *>(w + L.off_counters);
+    g.slots = reinterpret_cast<u64 *>(w + L.off_slots);
+    g.scratch = reinterpret_cast<float *>(w + L.off_scratch);
+    g.B = (u32)B;
+    g.n = (u32)n;
+    g.dim = (u32)dim;
+    g.k = (u32)k;
+    g.n_starts = (u32)(d_starts ? n_starts : 0);
+    set_plan("vanilla_grid_kernel clouds=%zu groups=%u G=%u slice=%u smem=%zu", B, L.gp.groups, L.gp.G, L.gp.slice,
+             L.gp.smem);
+    CK(launch_vanilla_grid(L.gp, g, st));
+    count_launch();
+    return FPS_OK;
+}
+
+static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts, size_t h,
+                          u64 *d_out, u32 *perm_out, u32 *leaf_lo_out, float *leaf_box_out, void *ws,
+                          size_t ws_bytes, int n_sms, cudaStream_t st) {
+    KdlinePlan pl;
+    CK(plan_kdline(n, dim, h, B, n_sms, &pl));
+    if (!ws || ws_bytes < pl.ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", pl.ws_bytes, ws_bytes);
+        return FPS_ERR_WORKSPACE;
+    }
+    KdlineArgs a;
+    memset(&a, 0, sizeof(a));
+    a.pts = d_pts;
+    a.starts = d_starts;
+    a.out = d_out;
+    a.perm_out = perm_out;
+    a.leaf_lo_out = leaf_lo_out;
+    a.leaf_box_out = leaf_box_out;
+    a.B = (u32)B;
+    a.n = (u32)n;
+    a.dim = (u32)dim;
+    a.k = (u32)k;
+    a.h = (u32)h;
+    set_plan("kdline_kernel<DIM=%d> clouds=%zu grid=%u threads=%u smem=%zu placement=%s ws/cta=%zu", pl.dimp, B, pl.grid,
+             pl.threads, pl.smem, pl.in_smem == 3 ? "smem" : (pl.in_smem == 2 ? "meta-smem,data-L2" : "L2"),
+             pl.ws_stride);
+    CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+    return FPS_OK;
+}
+
+// ---- host-pointer shard on one device ------------------------------------------------------------------------------
+struct ShardJob {
+    int algo;
+    const float *pts;
+    size_t B, n, dim, k, h;
+    const size_t *start;  // per cloud [B][n_starts] or nullptr
+    size_t n_starts;
+    size_t *out;
+};
+
+static int run_shard(int dev, const ShardJob &j) {
+    DevCtx *cx = get_ctx(dev);
+    if (!cx) {
+        set_err("device %d is not a usable sm_100 device", dev);
+        return FPS_ERR_NO_DEVICE;
+    }
+    std::lock_guard<std::mutex> lk(cx->mu);
+    CK(cudaSetDevice(dev));
+    if (!cx->ready) {
+        for (auto &ln : cx->lane) CK(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        cx->ready = true;
+    }
+    const size_t in_per = j.n * j.dim * sizeof(float), out_per = j.k * sizeof(u64);
+    const size_t nch = j.B >= 256 ? 4 : (j.B >= 64 ? 2 : 1);
+    const size_t chunk = (j.B + nch - 1) / nch;
+    static_assert(sizeof(size_t) == sizeof(u64), "size_t must be 64-bit");
+    int rc = FPS_OK;
+    for (size_t c = 0, b0 = 0; b0 < j.B && rc == FPS_OK; ++c, b0 += chunk) {
+        const size_t nb = (j.B - b0 < chunk) ? j.B - b0 : chunk;
+        Lane &ln = cx->lane[c & 1];
+        size_t ws_need;
+        if (j.algo == FPS_ALGO_VANILLA) {
+            WsLayout L;
+            vanilla_layout(nb, j.n, j.dim, cx->n_sms, &L);
+            ws_need = L.total;
+        } else {
+            KdlinePlan pl;
+            CK(plan_kdline(j.n, j.dim, j.h, nb, cx->n_sms, &pl));
+            ws_need = pl.ws_bytes;
+        }
+        if ((rc = ln.in.ensure(nb * in_per)) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) break;
+        u64 *d_starts = nullptr;
+        if (j.start) {
+            if ((rc = ln.starts.ensure(nb * j.n_starts * sizeof(u64)))) break;
+            d_starts = static_cast<u64 *>(ln.starts.p);
+            CK(cudaMemcpyAsync(d_starts, j.start + b0 * j.n_starts, nb * j.n_starts * sizeof(u64),
+                               cudaMemcpyHostToDevice, ln.st));
+        }
+        CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
+        if (j.algo == FPS_ALGO_VANILLA)
+            rc = enqueue_vanilla(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.n_starts,
+                                 static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
+        else
+            rc = enqueue_kdline(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.h,
+                                static_cast<u64 *>(ln.out.p), nullptr, nullptr, nullptr, ln.ws.p, ln.ws.cap,
+                                cx->n_sms, ln.st);
+        if (rc) break;
+        CK(cudaMemcpyAsync(j.out + b0 * j.k, ln.out.p, nb * out_per, cudaMemcpyDeviceToHost, ln.st));
+    }
+    for (auto &ln : cx->lane) {
+        cudaError_t e = cudaStreamSynchronize(ln.st);
+        if (e != cudaSuccess && rc == FPS_OK) {
+            set_err("kernel execution failed: %s", cudaGetErrorString(e));
+            rc = FPS_ERR_CUDA + (int)e;
+        }
+    }
+    return rc;
+}
+
+static int run_batch(ShardJob j, const int *devices, int n_devices) {
+    scan_devices();
+    std::vector<int> devs;
+    if (devices && n_devices > 0)
+        devs.assign(devices, devices + n_devices);
+    else
+        devs = g_devs;
+    if (devs.empty()) {
+        set_err("no usable CUDA device (need compute capability 10.x); there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    for (int d : devs)
+        if (!get_ctx(d)) {
+            set_err("device %d is not a usable sm_100 device", d);
+            return FPS_ERR_NO_DEVICE;
+        }
+    size_t G = devs.size();
+    if (G > j.B) G = j.B;
+    if (G == 1) return run_shard(devs[0], j);
+    // contiguous shards, remainder to the low ranks; no inter-device traffic
+    std::vector<int> rcs(G, FPS_OK);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    size_t base = j.B / G, rem = j.B % G, b0 = 0;
+    for (size_t g = 0; g < G; ++g) {
+        size_t nb = base + (g < rem ? 1 : 0);
+        ShardJob s = j;
+        s.B = nb;
+        s.pts = j.pts + b0 * j.n * j.dim;
+        s.out = j.out + b0 * j.k;
+        s.start = j.start ? j.start + b0 * j.n_starts : nullptr;
+        int dev = devs[g];
+        th.emplace_back([&, g, s, dev]() {
+            rcs[g] = run_shard(dev, s);
+            if (rcs[g]) errs[g] = tl_err;
+        });
+        b0 += nb;
+    }
+    for (auto &t : th) t.join();
+    for (size_t g = 0; g < G; ++g)
+        if (rcs[g]) {
+            set_err("device %d: %s", devs[g], errs[g].c_str());
+            return rcs[g];
+        }
+    return FPS_OK;
+}
+
+}  // namespace fps
+
+using namespace fps;
+
+// ======================================================================================================
+//  exported C ABI
+// ======================================================================================================
+extern "C" {
+
+int fps_b200_device_count(void) {
+    scan_devices();
+    return (int)g_devs.size();
+}
+const char *fps_b200_version(void) { return "fpsample-b200 0.1.0 (sm_100a)"; }
+const char *fps_b200_last_error(void) { return tl_err; }
+const char *fps_b200_last_plan(void) { return tl_plan; }
+uint64_t fps_b200_kernel_launches(void) { return g_launches.load(); }
+
+void *fps_b200_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void fps_b200_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+int fps_b200_vanilla(const float *points, size_t n, size_t dim, size_t k, const size_t *starts, size_t n_starts,
+                     size_t *out) {
+    int rc = check_common(points, 1, n, dim, k, out);
+    if (rc) return rc;
+    if (!starts || n_starts == 0 || n_starts > k) {
+        set_err("need 1 <= n_starts <= k start indices (n_starts=%zu k=%zu)", n_starts, k);
+        return FPS_ERR_ARG;
+    }
+    for (size_t i = 0; i < n_starts; ++i)
+        if (starts[i] >= n) {
+            set_err("start index %zu out of range (n=%zu)", starts[i], n);
+            return FPS_ERR_START;
+        }
+    ShardJob j{FPS_ALGO_VANILLA, points, 1, n, dim, k, 0, starts, n_starts, out};
+    return run_batch(j, nullptr, 1);
+}
+
+int bucket_fps_kdline(const float *raw_data, size_t n_points, size_t dim, size_t n_samples, size_t start_idx,
+                      size_t height, size_t *out) {
+    // same order and codes as src/wrapper.hpp:121-127
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    if (start_idx >= n_points) {
+        set_err("start_idx %zu out of range (n=%zu)", start_idx, n_points);
+        return FPS_ERR_START;
+    }
+    int rc = check_common(raw_data, 1, n_points, dim, n_samples, out);
+    if (rc) return rc;
+    if ((rc = check_kdline(n_points, dim, height))) return rc;
+    ShardJob j{FPS_ALGO_KDLINE, raw_data, 1, n_points, dim, n_samples, height, &start_idx, 1, out};
+    return run_batch(j, nullptr, 1);
+}
+
+int fps_b200_vanilla_batch(const float *points, size_t B, size_t n, size_t dim, size_t k, const size_t *start,
+                           size_t *out, const int *devices, int n_devices) {
+    int rc = check_common(points, B, n, dim, k, out);
+    if (rc) return rc;
+    if (start)
+        for (size_t b = 0; b < B; ++b)
+            if (start[b] >= n) {
+                set_err("start[%zu]=%zu out of range (n=%zu)", b, start[b], n);
+                return FPS_ERR_START;
+            }
+    ShardJob j{FPS_ALGO_VANILLA, points, B, n, dim, k, 0, start, 1, out};
+    return run_batch(j, devices, n_devices);
+}
+
+int fps_b200_kdline_batch(const float *points, size_t B, size_t n, size_t dim, size_t k, const size_t *start,
+                          size_t height, size_t *out, const int *devices, int n_devices) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    if (start)
+        for (size_t b = 0; b < B; ++b)
+            if (start[b] >= n) {
+                set_err("start[%zu]=%zu out of range (n=%zu)", b, start[b], n);
+                return FPS_ERR_START;
+            }
+    int rc = check_common(points, B, n, dim, k, out);
+    if (rc) return rc;
+    if ((rc = check_kdline(n, dim, height))) return rc;
+    ShardJob j{FPS_ALGO_KDLINE, points, B, n, dim, k, height, start, 1, out};
+    return run_batch(j, devices, n_devices);
+}
+
+size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t k, size_t height) {
+    (void)k;
+    int n_sms = n_sms_current(nullptr);
+    if (n_sms <= 0 || B == 0 || n == 0 || dim == 0) return 0;
+    if (algo == FPS_ALGO_VANILLA) {
+        WsLayout L;
+        vanilla_layout(B, n, dim, n_sms, &L);
+        return L.total;
+    }
+    if (dim > FPS_B200_MAX_KDLINE_DIM || check_kdline(n, dim, height)) return 0;
+    KdlinePlan pl;
+    if (plan_kdline(n, dim, height, B, n_sms, &pl) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return pl.ws_bytes;
+}
+
+int fps_b200_vanilla_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k,
+                               const uint64_t *d_start, uint64_t *d_out, void *d_workspace, size_t workspace_bytes,
+                               void *stream) {
+    int rc = check_common(d_points, B, n, dim, k, d_out);
+    if (rc) return rc;
+    int n_sms = n_sms_current(nullptr);
+    if (n_sms <= 0) {
+        set_err("current device is not a usable sm_100 device; there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    return enqueue_vanilla(d_points, B, n, dim, k, reinterpret_cast<const u64 *>(d_start), 1,
+                           reinterpret_cast<u64 *>(d_out), d_workspace, workspace_bytes, n_sms,
+                           static_cast<cudaStream_t>(stream));
+}
+
+int fps_b200_kdline_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k, const uint64_t *d_start,
+                              size_t height, uint64_t *d_out, void *d_workspace, size_t workspace_bytes,
+                              void *stream) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    int rc = check_common(d_points, B, n, dim, k, d_out);
+    if (rc) return rc;
+    if ((rc = check_kdline(n, dim, height))) return rc;
+    int n_sms = n_sms_current(nullptr);
+    if (n_sms <= 0) {
+        set_err("current device is not a usable sm_100 device; there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    return enqueue_kdline(d_points, B, n, dim, k, reinterpret_cast<const u64 *>(d_start), height,
+                          reinterpret_cast<u64 *>(d_out), nullptr, nullptr, nullptr, d_workspace, workspace_bytes, n_sms,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int fps_b200_kdline_build_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t height, uint32_t *d_perm,
+                              uint32_t *d_leaf_lo, float *d_leaf_box, void *d_workspace, size_t workspace_bytes,
+                              void *stream) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    int rc = check_common(d_points, B, n, dim, 1, d_perm);
+    if (rc) return rc;
+    if ((rc = check_kdline(n, dim, height))) return rc;
+    int n_sms = n_sms_current(nullptr);
+    if (n_sms <= 0) {
+        set_err("current device is not a usable sm_100 device; there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    return enqueue_kdline(d_points, B, n, dim, 1, nullptr, height, nullptr, d_perm, d_leaf_lo, d_leaf_box, d_workspace,
+                          workspace_bytes, n_sms, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// engine.h -- internal interface between the kernel translation units and the C-ABI layer.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace fps {
+
+typedef unsigned long long u64;
+typedef unsigned int u32;
+
+// ---- vanilla -------------------------------------------------------------------------------------------
+struct VanillaArgs {
+    const float *pts;   // [B][n][dim] row-major
+    const u64 *starts;  // nullptr (start 0) or [B][n_starts]
+    u64 *out;           // [B][k]
+    u32 n, dim, k, n_starts;
+    u32 slice;          // points per CTA of a cluster
+};
+
+struct VanillaPlan {
+    int dimp, ppt;
+    u32 C, slice;
+    size_t smem;
+};
+
+struct VanillaGridArgs {
+    const float *pts;
+    const u64 *starts;
+    u64 *out;
+    float *scratch;   // per-CTA [dim+1][slice] when the slice does not fit in shared memory
+    u64 *slots;       // [groups][2][G]
+    u32 *counters;    // [groups][32]
+    u32 B, n, dim, k, n_starts;
+    u32 G, slice, use_smem;
+};
+
+struct VanillaGridPlan {
+    u32 G, groups, slice;
+    bool use_smem;
+    size_t smem, scratch_floats;
+};
+
+bool plan_vanilla_cluster(size_t n, size_t dim, size_t B, int n_sms, VanillaPlan *pl);
+cudaError_t launch_vanilla_cluster(const VanillaPlan &pl, VanillaArgs a, u32 B, cudaStream_t st);
+void plan_vanilla_grid(size_t n, size_t dim, size_t B, int n_sms, VanillaGridPlan *pl);
+cudaError_t launch_vanilla_grid(const VanillaGridPlan &pl, VanillaGridArgs a, cudaStream_t st);
+
+// ---- kd-line -------------------------------------------------------------------------------------------
+struct KdlineArgs {
+    const float *pts;   // [B][n][dim]
+    const u64 *starts;  // nullptr or [B] (POSITION in the permuted array, src/wrapper.hpp:54-55)
+    u64 *out;           // [B][k] or nullptr (build only)
+    unsigned char *ws;  // per-cloud workspace region base (global), ws_stride bytes each
+    size_t ws_stride;
+    // optional build outputs (nullptr unless the build-only entry asked for them)
+    u32 *perm_out;      // [B][n]
+    u32 *leaf_lo_out;   // [B][2^h+1]
+    float *leaf_box_out;// [B][2^h][2][dim]
+    u32 B, n, dim, k, h;
+    u32 in_smem;        // bit0: coordinates + scratch in shared memory, bit1: node/bucket metadata in shared memory
+};
+
+struct KdlinePlan {
+    int dimp;
+    u32 threads, in_smem, grid;
+    size_t smem;        // dynamic shared memory bytes
+    size_t ws_stride;   // global workspace bytes per resident CTA
+    size_t ws_bytes;    // total workspace: 256-byte work counter + grid * ws_stride
+};
+
+cudaError_t plan_kdline(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdlinePlan *pl);
+cudaError_t launch_kdline(const KdlinePlan &pl, KdlineArgs a, unsigned char *ws_base, cudaStream_t st);
+
+void count_launch();
+
+}  // namespace fps

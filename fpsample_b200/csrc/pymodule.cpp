@@ -1,0 +1,157 @@
+// pymodule.cpp -- pybind11 module `_fpsample`: the host-side mirror of the reference's binding layer for
+// the two hot entry points (src/lib.cpp:249-270 `_fps_sampling`, :522-579 `_bucket_fps_kdline_sampling`),
+// same positional signatures, same exception types, numpy arrays in, uint64 index arrays out.  All
+// compute goes through the C ABI in include/fps_b200.h; there is no CPU path in this file.
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "../../include/fps_b200.h"
+
+namespace py = pybind11;
+using farray = py::array_t<float, py::array::c_style | py::array::forcecast>;
+using iarray = py::array_t<size_t, py::array::c_style | py::array::forcecast>;
+
+static void raise_rc(const char *fn, int rc) {
+    // the reference surfaces a non-zero C return code as RuntimeError (src/lib.cpp:574-576)
+    std::string msg = std::string(fn) + " failed with error code " + std::to_string(rc);
+    const char *why = fps_b200_last_error();
+    if (why && *why) msg += std::string(": ") + why;
+    throw std::runtime_error(msg);
+}
+
+// src/lib.cpp:249-270 + check_py_input (:52-109)
+static py::array_t<size_t> fps_sampling_py(farray points, size_t n_samples, py::object start_idx_obj) {
+    std::vector<size_t> starts;
+    if (py::isinstance<py::int_>(start_idx_obj)) {
+        starts.push_back(start_idx_obj.cast<size_t>());
+    } else if (py::isinstance<py::array_t<size_t>>(start_idx_obj)) {
+        auto arr = start_idx_obj.cast<py::array_t<size_t>>();
+        if (arr.ndim() != 1) throw py::type_error("start_idx must be int or 1D numpy array of size_t");
+        auto v = arr.unchecked<1>();
+        for (py::ssize_t i = 0; i < v.shape(0); ++i) starts.push_back(v(i));
+        if (starts.empty()) throw py::value_error("start_idx array must not be empty");
+    } else {
+        throw py::type_error("start_idx must be int or 1D numpy array of size_t");
+    }
+    if (points.ndim() != 2)
+        throw py::value_error("points must be a 2D array, but got shape " + std::to_string(points.ndim()));
+    const size_t P = (size_t)points.shape(0), C = (size_t)points.shape(1);
+    if (C == 0) throw py::value_error("points must have at least one column");
+    if (n_samples > P)
+        throw py::value_error("n_samples must be less than the number of points: n_samples=" +
+                              std::to_string(n_samples) + ", P=" + std::to_string(P));
+    if (starts.size() > n_samples && !(starts.size() == 1 && n_samples == 0))
+        throw py::value_error("The number of start indices must be less than or equal to n_samples: " +
+                              std::to_string(starts.size()) + ", n_samples=" + std::to_string(n_samples));
+    for (size_t s : starts)
+        if (s >= P)
+            throw py::value_error("start_idx must be less than the number of points: start_idx=" + std::to_string(s) +
+                                  ", P=" + std::to_string(P));
+    py::array_t<size_t> out(n_samples);
+    if (n_samples == 0) return out;
+    int rc;
+    {
+        const float *src = points.data();
+        size_t *dst = out.mutable_data();
+        py::gil_scoped_release rel;
+        rc = fps_b200_vanilla(src, P, C, n_samples, starts.data(), starts.size(), dst);
+    }
+    if (rc != 0) raise_rc("fps_b200_vanilla", rc);
+    return out;
+}
+
+// src/lib.cpp:522-579
+static py::array_t<size_t> kdline_py(farray points, size_t n_samples, size_t height, py::object start_idx_obj) {
+    size_t start = 0;
+    if (py::isinstance<py::int_>(start_idx_obj)) {
+        start = start_idx_obj.cast<size_t>();
+    } else if (py::isinstance<py::array_t<size_t>>(start_idx_obj)) {
+        PyErr_SetString(PyExc_NotImplementedError, "Array of start indices not implemented yet");
+        throw py::error_already_set();
+    } else {
+        throw py::type_error("start_idx must be int or 1D numpy array of size_t");
+    }
+    if (points.ndim() != 2) throw py::value_error("points must be a 2D float32 array");
+    const size_t P = (size_t)points.shape(0), C = (size_t)points.shape(1);
+    if (start >= P) throw py::value_error("start_idx out of range");
+    if (n_samples == 0 || n_samples > P) throw py::value_error("n_samples must be in [1, num_points]");
+    if (height == 0) throw py::value_error("height must be >= 1");
+    py::array_t<size_t> out(n_samples);
+    int rc;
+    {
+        const float *src = points.data();
+        size_t *dst = out.mutable_data();
+        py::gil_scoped_release rel;
+        rc = bucket_fps_kdline(src, P, C, n_samples, start, height, dst);
+    }
+    if (rc != 0) raise_rc("bucket_fps_kdline", rc);
+    return out;
+}
+
+// ---- batched entries (new) -----------------------------------------------------------------------------
+static std::vector<size_t> batch_starts(py::object start_obj, size_t B, size_t P) {
+    std::vector<size_t> st;
+    if (start_obj.is_none()) return st;
+    if (py::isinstance<py::int_>(start_obj)) {
+        st.assign(B, start_obj.cast<size_t>());
+    } else {
+        auto arr = iarray::ensure(start_obj);
+        if (!arr || arr.ndim() != 1 || (size_t)arr.shape(0) != B)
+            throw py::type_error("start_idx must be None, int or a 1D integer array of length B");
+        st.assign(arr.data(), arr.data() + B);
+    }
+    for (size_t s : st)
+        if (s >= P) throw py::value_error("start_idx out of range");
+    return st;
+}
+
+static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, size_t height, py::object start_obj,
+                                    py::object devices_obj) {
+    if (points.ndim() != 3) throw py::value_error("points must be a 3D array [B, N, D]");
+    const size_t B = (size_t)points.shape(0), P = (size_t)points.shape(1), C = (size_t)points.shape(2);
+    if (B == 0) throw py::value_error("batch must hold at least one cloud");
+    if (C == 0) throw py::value_error("points must have at least one column");
+    if (n_samples == 0 || n_samples > P) throw py::value_error("n_samples must be in [1, num_points]");
+    if (algo == FPS_ALGO_KDLINE && height == 0) throw py::value_error("height must be >= 1");
+    std::vector<size_t> st = batch_starts(start_obj, B, P);
+    std::vector<int> devs;
+    if (!devices_obj.is_none()) devs = devices_obj.cast<std::vector<int>>();
+    py::array_t<size_t> out({(py::ssize_t)B, (py::ssize_t)n_samples});
+    int rc;
+    {
+        const float *src = points.data();
+        size_t *dst = out.mutable_data();
+        const size_t *sp = st.empty() ? nullptr : st.data();
+        const int *dp = devs.empty() ? nullptr : devs.data();
+        py::gil_scoped_release rel;
+        if (algo == FPS_ALGO_VANILLA)
+            rc = fps_b200_vanilla_batch(src, B, P, C, n_samples, sp, dst, dp, (int)devs.size());
+        else
+            rc = fps_b200_kdline_batch(src, B, P, C, n_samples, sp, height, dst, dp, (int)devs.size());
+    }
+    if (rc != 0) raise_rc(algo == FPS_ALGO_VANILLA ? "fps_b200_vanilla_batch" : "fps_b200_kdline_batch", rc);
+    return out;
+}
+
+PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
+    m.doc() = "B200-native farthest point sampling: drop-in for fpsample._fpsample's FPS hot path";
+    m.def("_fps_sampling", &fps_sampling_py,
+          "Vanilla FPS. points: N x C float32; n_samples; start_idx: int or 1D uint64 array. Returns uint64[n_samples].");
+    m.def("_bucket_fps_kdline_sampling", &kdline_py,
+          "QuickFPS kd-line. points: N x C float32 (C <= 8); n_samples; height; start_idx: int. Returns uint64[n_samples].");
+    m.def("_fps_sampling_batch",
+          [](farray p, size_t k, py::object s, py::object d) { return batch_py(FPS_ALGO_VANILLA, p, k, 0, s, d); },
+          "Batched vanilla FPS. points: B x N x C; start_idx: None|int|int[B]; devices: None|list[int].");
+    m.def("_bucket_fps_kdline_sampling_batch",
+          [](farray p, size_t k, size_t h, py::object s, py::object d) { return batch_py(FPS_ALGO_KDLINE, p, k, h, s, d); },
+          "Batched QuickFPS kd-line. points: B x N x C; height; start_idx: None|int|int[B]; devices: None|list[int].");
+    m.def("_device_count", []() { return fps_b200_device_count(); });
+    m.def("_last_plan", []() { return std::string(fps_b200_last_plan()); });
+    m.def("_kernel_launches", []() { return fps_b200_kernel_launches(); });
+    m.attr("__version__") = "1.0.2+b200.0.1.0";
+}
