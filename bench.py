@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""bench.py -- the measurement contract of this repo (one JSON line on stdout, rank 0).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg1|cfg3|cfg4|cfg4l|cfg5d3|cfg5d6]
+                  [--algo kdline|vanilla] [--impl b200|reference] [--no-extras]
+  N > 1:  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 ... bench.py --gpus N
+
+A "step" is one pass of the FPS hot path over one batch of synthetic clouds (BASELINE.json configs; default
+cfg2 = `bucket_fps_kdline_sampling` 4096x3 -> 1024, h=5, batch of 1024 clouds PER GPU -- weak scaling: clouds are
+independent, every rank samples its own shard, no data-path collective; indices are gathered to rank 0 over
+NCCL once, after the timed region, as a correctness sanity only).
+
+  value  : clouds/s, inputs already resident in HBM, device pointers through the C ABI (*_batch_dev), timed with
+           CUDA events on the launching stream, per step, L2 flushed between steps; max over ranks.
+  e2e    : the same metric through the public python API (fpsample_b200.*_batch) with HOST (pinned) buffers:
+           H2D of the clouds and D2H of the indices inside the timed region, every step.
+  roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md section "Measurement".
+
+torch is used for device buffers, events, streams and torch.distributed only.  The oracle (oracle/) is
+executed here ONLY in the cpu_baseline leg, the `--impl reference` arm and the post-run sanity check.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, n, d, k, h, generator, base seed, BASELINE.json config it is)
+    "cfg1": (1, 4096, 3, 1024, 5, "uniform", 1, "configs[0] fps_sampling 4096x3->1024 single cloud"),
+    "cfg2": (1024, 4096, 3, 1024, 5, "uniform", 1000, "configs[1] 4096x3->1024, h=5, batch of 1024 clouds"),
+    "cfg3": (64, 16384, 3, 4096, 7, "uniform", 2000, "configs[2] PointNet++ SA batch B=64 x 16384x3->4096, h=7"),
+    "cfg4": (1, 2**20, 3, 65536, 9, "uniform", 5, "configs[3] single cloud 1,048,576x3->65536, h=9 (uniform)"),
+    "cfg4l": (1, 2**20, 3, 65536, 9, "lidar", 6, "configs[3] single LiDAR-like cloud 1,048,576x3->65536, h=9"),
+    "cfg5d3": (4096, 100000, 3, 8192, 7, "uniform", 3000, "configs[4] batch of 4096 clouds x 100k x3 -> 8192"),
+    "cfg5d6": (4096, 100000, 6, 8192, 7, "uniform", 3000, "configs[4] batch of 4096 clouds x 100k x6 -> 8192"),
+}
+SM_COUNT, LANES = 148, 128
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md)"
+
+
+def make_cloud(gen, seed, n, d):
+    from fpsample_b200 import synth
+    return synth.lidar(seed, n) if gen == "lidar" else synth.uniform(seed, n, d)
+
+
+# ---- CPU arm: the reference's own implementation on the host cores, one cloud per core ----------------------
+_REF = None
+_CLOUDS = []   # generated in the parent BEFORE the pool forks: workers inherit them, timers see compute only
+
+
+def _cpu_init():
+    global _REF
+    from oracle import oracle as O
+    r = O.load_reference()
+    _REF = ("reference", r) if r is not None else ("port", O)
+
+
+def _cpu_one(task):
+    algo, i, k, h = task
+    pc = _CLOUDS[i]
+    kind, m = _REF
+    t = time.perf_counter()
+    if kind == "reference":
+        out = m.fps_sampling(pc, k, 0) if algo == "vanilla" else m.bucket_fps_kdline_sampling(pc, k, h, 0)
+    else:
+        out = m.fps_vanilla(pc, k, 0) if algo == "vanilla" else m.kdline(pc, k, h, 0)
+    return time.perf_counter() - t, int(out[-1])
+
+
+class CpuArm:
+    """multiprocessing pool over all host cores (the reference holds the GIL: processes, not threads).
+    A bounded sample of the workload's clouds is generated up front; run() = pool.map over it, wall-clock."""
+
+    def __init__(self, algo, wl, budget_s):
+        import multiprocessing as mp
+        global _CLOUDS
+        self.algo, self.wl = algo, wl
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        B, n, d, k, h, gen, seed, _ = WORKLOADS[wl]
+        self.workers = max(1, min(self.cores, B))
+        _cpu_init()
+        self.kind = _REF[0]
+        _CLOUDS = [make_cloud(gen, seed, n, d)]
+        self.t1 = min(_cpu_one((algo, 0, k, h))[0] for _ in range(2 if n * k < 1e9 else 1))   # probe, one core
+        waves = max(1, int(budget_s / max(self.t1 * 1.5, 1e-4)))
+        self.n_clouds = max(1, min(B, self.workers * waves, max(self.workers, int(2e9 // (n * d * 4)))))
+        _CLOUDS = [make_cloud(gen, seed + i, n, d) for i in range(self.n_clouds)]
+        self.reps = max(1, min(50, int(budget_s * self.workers / max(self.t1 * 1.5 * self.n_clouds, 1e-4))))
+        self.pool = mp.get_context("fork").Pool(self.workers, initializer=_cpu_init)
+        self.pool.map(_cpu_one, [(algo, i % self.n_clouds, k, h) for i in range(self.workers)], chunksize=1)  # warm
+
+    def run(self):
+        """one pass over the sample -> (wall seconds, clouds done, mean per-cloud compute seconds)"""
+        B, n, d, k, h, gen, seed, _ = WORKLOADS[self.wl]
+        tasks = [(self.algo, i, k, h) for i in range(self.n_clouds)]
+        cs = max(1, self.n_clouds // (self.workers * 8))
+        t = time.perf_counter()
+        res = self.pool.map(_cpu_one, tasks, chunksize=cs)
+        wall = time.perf_counter() - t
+        return wall, self.n_clouds, statistics.mean(r[0] for r in res)
+
+    def describe(self, per):
+        return (f"{self.n_clouds} clouds of the workload per pass, one cloud per core on {self.workers} of {self.cores} "
+                f"host cores, mean {per * 1e3:.3f} ms/cloud/core under load ({self.t1 * 1e3:.3f} ms alone), "
+                f"{'compiled unmodified reference' if self.kind == 'reference' else 'C oracle port'}, {self.algo}")
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def cpu_measure(arm: CpuArm):
+    walls, pers = [], []
+    for _ in range(arm.reps):
+        w, done, per = arm.run()
+        walls.append(w)
+        pers.append(per)
+    thr = arm.n_clouds * len(walls) / sum(walls)
+    return dict(value=thr, unit="clouds/s", cores=arm.workers, kind=arm.kind,
+                sample=f"{len(walls)} passes; " + arm.describe(statistics.mean(pers)),
+                ms_per_cloud_per_core=statistics.mean(pers) * 1e3)
+
+
+# ---- clocks sampler ------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, dev):
+        self.dev, self.rows, self.p = dev, [], None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.dev), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---- GPU arm ---------------------------------------------------------------------------------------------------
+def algorithmic_work(algo, wl, sample=8):
+    """per-cloud algorithmic work: point-updates and bucket tests of the REFERENCE
+    algorithm (oracle counters on a seeded sample of the workload's clouds); vanilla: n*(k-1) exactly."""
+    B, n, d, k, h, gen, seed, _ = WORKLOADS[wl]
+    if algo == "vanilla":
+        return float(n) * (k - 1), 0.0
+    from oracle import oracle as O
+    pu = bt = 0
+    m = min(sample, B)
+    for i in range(m):
+        _, st = O.kdline(make_cloud(gen, seed + i, n, d), k, h, 0, return_stats=True)
+        pu += st["point_updates"]
+        bt += st["bucket_tests"]
+    return pu / m, bt / m
+
+
+def gpu_arm(args):
+    import torch
+    import fpsample_b200 as fps
+    from fpsample_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    B, n, d, k, h, gen, seed, desc = WORKLOADS[args.workload]
+    algo = args.algo
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:   # before CUDA init: the pool forks
+        arm = CpuArm(algo, args.workload, args.cpu_budget)
+        cpu = cpu_measure(arm)
+        arm.close()
+
+    if capi.device_count() < 1:
+        raise SystemExit("bench.py: no sm_100 device visible; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    # this rank's shard: B clouds, globally distinct seeds (weak scaling)
+    host = capi.pinned_empty((B, n, d), np.float32)
+    for b in range(B):
+        host[b] = make_cloud(gen, seed + rank * B + b, n, d)
+    dpts = torch.from_numpy(host).to(dev)
+    dout = torch.empty((B, k), dtype=torch.int64, device=dev)
+    a = capi.ALGO_VANILLA if algo == "vanilla" else capi.ALGO_KDLINE
+    wsb = capi.workspace_bytes(a, B, n, d, k, h)
+    ws = torch.empty(wsb + 512, dtype=torch.uint8, device=dev)
+    wp = (ws.data_ptr() + 255) & ~255
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.Stream(device=dev)
+
+    def launch():
+        if algo == "vanilla":
+            capi.vanilla_batch_dev(dpts.data_ptr(), B, n, d, k, 0, dout.data_ptr(), wp, wsb, stream.cuda_stream)
+        else:
+            capi.kdline_batch_dev(dpts.data_ptr(), B, n, d, k, 0, h, dout.data_ptr(), wp, wsb, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            launch()
+    barrier()
+    plan = capi.last_plan()
+
+    clocks = Clocks(local)
+    clocks.start()
+    l0 = capi.kernel_launches()
+    evs = []
+    barrier()
+    with torch.cuda.stream(stream):
+        for _ in range(args.steps):
+            flush.fill_(1)                                  # L2 flush, outside the event pair
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            launch()
+            e1.record(stream)
+            evs.append((e0, e1))
+    barrier()
+    launches = capi.kernel_launches() - l0
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    dev_ms = maxr(sum(step_ms))                             # K steps, max over ranks
+    ms_per_step = dev_ms / args.steps
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    dev_idx = dout.cpu().numpy().astype(np.uint64)
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region ------------------------------------
+    api = (lambda: fps.fps_sampling_batch(host, k, 0, devices=[local])) if algo == "vanilla" else \
+          (lambda: fps.bucket_fps_kdline_sampling_batch(host, k, h, 0, devices=[local]))
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_idx = api()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_idx = api()
+    torch.cuda.synchronize()
+    e2e_s = maxr(time.perf_counter() - t0)
+    barrier()
+    clk = clocks.stop()
+    e2e_value = world * B * args.steps / e2e_s
+    same = bool(np.array_equal(e2e_idx, dev_idx))
+
+    # ---- sanity: gather to rank 0 (NCCL), check a few clouds against the oracle --------------------------------
+    from fpsample_b200 import dist as D
+    allidx = D.gather_indices(dev_idx, world * B, device=dev) if world > 1 else dev_idx
+    checked = 0
+    if rank == 0:
+        from oracle import oracle as O
+        for b in sorted({0, B - 1, (world - 1) * B, world * B - 1}):
+            pc = make_cloud(gen, seed + b, n, d)
+            if algo == "kdline":
+                ok = np.array_equal(allidx[b], O.kdline(pc, k, h, 0))
+            else:
+                ok = O.certify_vanilla(pc, allidx[b])[0] if n * k > 2e8 else np.array_equal(allidx[b], O.fps_vanilla(pc, k, 0))
+            if not ok:
+                raise SystemExit(f"bench.py: cloud {b} differs from the oracle -- the number would be invalid")
+            checked += 1
+
+    # ---- roofline ----------------------------------------------------------------------------------------------
+    line = None
+    if rank == 0:
+        hbm_gbs, sm_mhz, how = peaks()
+        fp32_peak = SM_COUNT * LANES * sm_mhz * 1e6 / 1e12        # T lane-op/s, no FMA allowed on this path
+        pu, bt = algorithmic_work(algo, args.workload)
+        ops_cloud = pu * (3 * d + 1) + bt * (8 * d)
+        t_launch = (statistics.mean(step_ms) * 1e-3)               # one launch per step on this rank
+        fp32_ach = ops_cloud * B / t_launch / 1e12
+        bytes_cloud = n * d * 4 + k * 8
+        hbm_ach = bytes_cloud * B / t_launch / 1e9
+        bf_ops = float(n) * (k - 1) * (3 * d + 1) * B
+        line = {
+            "metric": "clouds/sec (BxN->K)", "value": value, "unit": "clouds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}; entry={'fps_sampling' if algo == 'vanilla' else 'bucket_fps_kdline_sampling'} (batched), "
+                                   f"start_idx=0, {B} clouds per GPU, seeds {seed}+i",
+                       "clouds_per_gpu": B, "n": n, "d": d, "k": k, "h": h if algo == "kdline" else None, "algo": algo,
+                       "l2": "inputs (%.0f MB/GPU) < L2: 256 MiB flush write between timed steps, outside the per-step CUDA-event pairs" % (B * n * d * 4 / 1e6),
+                       "plan": plan, "parallelism": f"dp{world} (independent clouds, contiguous shards, no data-path collective)"},
+            "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": B * n * d * 4,
+                    "d2h_bytes_per_step": B * k * 8, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "fpsample_b200.%s(host ndarray) -> host ndarray" % ("fps_sampling_batch" if algo == "vanilla" else "bucket_fps_kdline_sampling_batch"),
+                    "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "Tlaneop/s",
+                         "frac": fp32_ach / fp32_peak, "traffic": None,
+                         "kernel": plan.split(" ")[0],
+                         "note": f"governing roofline per SURVEY.md 8(d): FP32 pipe without FMA = 148 SM x 128 lanes x {sm_mhz:.0f} MHz ({how}); "
+                                 f"algorithmic work = reference algorithm's {pu:.0f} point-updates x {3 * d + 1} + {bt:.0f} bucket tests x {8 * d} lane-ops per cloud",
+                         "brute_force_equiv_frac": bf_ops / t_launch / 1e12 / fp32_peak},
+            "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_gbs, "unit": "GB/s",
+                             "frac": hbm_ach / hbm_gbs, "traffic": None,
+                             "note": f"compulsory bytes only: {bytes_cloud} B per cloud (coords in, uint64 indices out); clouds stay on chip for all k rounds; peak {how}"},
+            "cpu_baseline": cpu,
+            "parity_checked_clouds": checked,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+def extras(args):
+    """single-cloud latency lines that BASELINE.json's metric also names (ms for 1M -> 64K), device-resident."""
+    import torch
+    from fpsample_b200 import capi
+    out = {}
+    for wl, algo, reps in (("cfg4", "kdline", 3), ("cfg4l", "kdline", 3), ("cfg1", "vanilla", 20), ("cfg1", "kdline", 20)):
+        B, n, d, k, h, gen, seed, desc = WORKLOADS[wl]
+        pc = make_cloud(gen, seed, n, d)
+        dp = torch.from_numpy(pc).cuda()
+        do = torch.empty((1, k), dtype=torch.int64, device="cuda")
+        a = capi.ALGO_VANILLA if algo == "vanilla" else capi.ALGO_KDLINE
+        wsb = capi.workspace_bytes(a, 1, n, d, k, h)
+        ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda")
+        wp = (ws.data_ptr() + 255) & ~255
+        st = torch.cuda.current_stream()
+        fn = (lambda: capi.vanilla_batch_dev(dp.data_ptr(), 1, n, d, k, 0, do.data_ptr(), wp, wsb, st.cuda_stream)) if algo == "vanilla" \
+            else (lambda: capi.kdline_batch_dev(dp.data_ptr(), 1, n, d, k, 0, h, do.data_ptr(), wp, wsb, st.cuda_stream))
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out[f"{wl}_{algo}"] = {"ms": min(ts), "ms_mean": statistics.mean(ts), "ns_per_pick": min(ts) * 1e6 / max(k - 1, 1),
+                               "what": desc, "plan": capi.last_plan()}
+    return out
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None
+    B, n, d, k, h, gen, seed, desc = WORKLOADS[args.workload]
+    arm = CpuArm(args.algo, args.workload, max(2.0, args.cpu_budget / max(args.steps, 1)))
+    for _ in range(args.warmup):
+        arm.run()
+    walls, pers = [], []
+    for _ in range(args.steps):                                    # a step = one pass over the bounded sample
+        w, done, per = arm.run()
+        walls.append(w)
+        pers.append(per)
+    value = arm.n_clouds * args.steps / sum(walls)
+    cb = dict(value=value, unit="clouds/s", cores=arm.workers, kind=arm.kind,
+              sample=f"{args.steps} steps; " + arm.describe(statistics.mean(pers)))
+    arm.close()
+    return {"impl": "reference", "metric": "clouds/sec (BxN->K)", "value": value, "unit": "clouds/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sum(walls) / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}; entry={'fps_sampling' if args.algo == 'vanilla' else 'bucket_fps_kdline_sampling'}, start_idx=0",
+                       "n": n, "d": d, "k": k, "h": h if args.algo == "kdline" else None, "algo": args.algo,
+                       "note": "the reference's own CPU implementation on this box's host cores (all of them, one cloud per core); "
+                               "wall-clock over the pool, inputs pre-generated"},
+            "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": "clouds/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--algo", default="kdline", choices=["kdline", "vanilla"])
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU-baseline work per core")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        line = reference_arm(args)
+    else:
+        line = gpu_arm(args)
+        if line is not None and int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_extras:
+            try:
+                line["extra"] = extras(args)
+            except Exception as e:  # extras never invalidate the main line
+                line["extra"] = {"error": repr(e)}
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -10,12 +10,16 @@ def uniform(seed: int, n: int, d: int = 3) -> np.ndarray:
 
 
 def lidar(seed: int, n: int) -> np.ndarray:
-    """Ring-structured 64-beam spinning-lidar-like cloud (density ~ 1/r, negative coordinates)."""
+    """Ring-structured 64-beam spinning-lidar-like cloud (density ~ 1/r, negative coordinates).
+
+    Trigonometry is evaluated in float64 and rounded once to float32, so the array is the same on every
+    host CPU (float32 SIMD sin/cos differ by an ulp between AVX2 and AVX-512 builds of numpy).
+    """
     g = np.random.default_rng(seed)
-    az = g.random(n, dtype=np.float32) * np.float32(2 * np.pi)
+    az = g.random(n, dtype=np.float32).astype(np.float64) * (2 * np.pi)
     beam = g.integers(0, 64, n)
-    el = np.deg2rad(-25.0 + beam * (28.0 / 63.0)).astype(np.float32)
-    r = np.float32(2.0) + np.float32(78.0) * g.random(n, dtype=np.float32) * g.random(n, dtype=np.float32)
+    el = np.deg2rad(-25.0 + beam * (28.0 / 63.0))
+    r = 2.0 + 78.0 * g.random(n, dtype=np.float32).astype(np.float64) * g.random(n, dtype=np.float32).astype(np.float64)
     xyz = np.stack([r * np.cos(el) * np.cos(az), r * np.cos(el) * np.sin(az), r * np.sin(el)], axis=1)
     return np.ascontiguousarray(xyz, dtype=np.float32)
 

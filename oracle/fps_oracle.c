@@ -359,3 +359,105 @@ int oracle_kdline_sample_eager(const float *pts, size_t n, size_t d, size_t k, s
     kdl_free(t);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Full-size CERTIFIER (test infrastructure).  Given a claimed pick sequence out[k], replays the
+ * recurrence of src/lib.cpp:211-238 (mode 0: dm = +inf, ties -> highest index) or of SURVEY.md A.4
+ * (mode 1: rows are already in permuted order, dm = FLT_MAX, ties -> lowest position) along the
+ * CLAIMED picks and checks that every free pick is the arg-max of the running min-distances.  By
+ * induction over t this holds iff out[] equals what the sequential reference loop produces, but the
+ * point range can be cut into independent chunks (the picks are known), so it runs on all host cores:
+ * each worker keeps its chunk's dm[] cache-resident for all k rounds and records its chunk-local
+ * winner per round; the winners are merged at the end.
+ * returns 0 = certified, 1 = mismatch (first bad round in *bad_round), 3 = bad sizes.
+ * ------------------------------------------------------------------------------------------------ */
+#include <pthread.h>
+
+typedef struct {
+    const float *pts;
+    size_t n, d, k, lo, hi;
+    const size_t *picks;
+    int mode;
+    float *best_val;  /* [k] chunk-local winner value per round (round 0 unused) */
+    size_t *best_idx; /* [k] */
+} cert_job_t;
+
+static void *cert_worker(void *arg) {
+    cert_job_t *j = (cert_job_t *)arg;
+    const size_t d = j->d, cnt = j->hi - j->lo;
+    float *dm = (float *)malloc((cnt ? cnt : 1) * sizeof(float));
+    for (size_t i = 0; i < cnt; ++i) dm[i] = j->mode == 0 ? INFINITY : FLT_MAX;
+    for (size_t t = 1; t < j->k; ++t) {
+        const float *q = j->pts + j->picks[t - 1] * d;
+        float best = -1.0f;
+        size_t bi = j->lo;
+        for (size_t i = 0; i < cnt; ++i) {
+            float v = sqdist(j->pts + (j->lo + i) * d, q, d);
+            float cur = dm[i];
+            cur = (v < cur) ? v : cur;
+            dm[i] = cur;
+            if (j->mode == 0 ? (cur >= best) : (cur > best)) {
+                best = cur;
+                bi = j->lo + i;
+            }
+        }
+        j->best_val[t] = best;
+        j->best_idx[t] = bi;
+    }
+    free(dm);
+    return NULL;
+}
+
+int oracle_certify_fps(const float *pts, size_t n, size_t d, size_t k, const size_t *picks,
+                       size_t n_forced, int mode, int n_threads, size_t *bad_round) {
+    if (n == 0 || d == 0 || k == 0 || k > n || n_forced == 0) return 3;
+    for (size_t t = 0; t < k; ++t)
+        if (picks[t] >= n) {
+            if (bad_round) *bad_round = t;
+            return 1;
+        }
+    if (n_threads < 1) n_threads = 1;
+    if ((size_t)n_threads > n) n_threads = (int)n;
+    cert_job_t *jobs = (cert_job_t *)calloc((size_t)n_threads, sizeof(cert_job_t));
+    pthread_t *th = (pthread_t *)calloc((size_t)n_threads, sizeof(pthread_t));
+    size_t chunk = (n + (size_t)n_threads - 1) / (size_t)n_threads;
+    for (int w = 0; w < n_threads; ++w) {
+        cert_job_t *j = &jobs[w];
+        j->pts = pts;
+        j->n = n;
+        j->d = d;
+        j->k = k;
+        j->lo = (size_t)w * chunk < n ? (size_t)w * chunk : n;
+        j->hi = j->lo + chunk < n ? j->lo + chunk : n;
+        j->picks = picks;
+        j->mode = mode;
+        j->best_val = (float *)malloc(k * sizeof(float));
+        j->best_idx = (size_t *)malloc(k * sizeof(size_t));
+        pthread_create(&th[w], NULL, cert_worker, j);
+    }
+    for (int w = 0; w < n_threads; ++w) pthread_join(th[w], NULL);
+    int rc = 0;
+    for (size_t t = n_forced; t < k && rc == 0; ++t) {
+        float best = -1.0f;
+        size_t bi = 0;
+        for (int w = 0; w < n_threads; ++w) { /* chunks in ascending index order */
+            if (jobs[w].hi == jobs[w].lo) continue;
+            float v = jobs[w].best_val[t];
+            if (mode == 0 ? (v >= best) : (v > best)) {
+                best = v;
+                bi = jobs[w].best_idx[t];
+            }
+        }
+        if (bi != picks[t]) {
+            rc = 1;
+            if (bad_round) *bad_round = t;
+        }
+    }
+    for (int w = 0; w < n_threads; ++w) {
+        free(jobs[w].best_val);
+        free(jobs[w].best_idx);
+    }
+    free(jobs);
+    free(th);
+    return rc;
+}

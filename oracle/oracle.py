@@ -25,7 +25,7 @@ def build(force: bool = False) -> str:
         os.makedirs(os.path.dirname(_LIB), exist_ok=True)
         subprocess.check_call(
             ["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-             src, "-o", _LIB, "-lm"])
+             src, "-o", _LIB, "-lm", "-lpthread"])
     return _LIB
 
 
@@ -39,8 +39,9 @@ def _load():
         L.oracle_kdline_build.argtypes = [fp, sz, sz, sz, szp, szp, fp, szp]
         L.oracle_kdline_sample.argtypes = [fp, sz, sz, sz, sz, sz, szp, ctypes.c_void_p]
         L.oracle_kdline_sample_eager.argtypes = [fp, sz, sz, sz, sz, sz, szp]
+        L.oracle_certify_fps.argtypes = [fp, sz, sz, sz, szp, sz, ctypes.c_int, ctypes.c_int, szp]
         for f in (L.oracle_fps_vanilla, L.oracle_kdline_build, L.oracle_kdline_sample,
-                  L.oracle_kdline_sample_eager):
+                  L.oracle_kdline_sample_eager, L.oracle_certify_fps):
             f.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -105,6 +106,38 @@ def kdline_eager(pc, k, h, start=0):
                                             out.ctypes.data)
     _check(rc, "oracle_kdline_sample_eager")
     return out
+
+
+def certify_vanilla(pc, picks, n_forced=1, n_threads=None):
+    """True iff `picks` is exactly what fps_sampling yields from picks[:n_forced] (all host cores)."""
+    pc = _f32(pc)
+    picks = np.ascontiguousarray(picks, dtype=np.uint64)
+    bad = ctypes.c_size_t(0)
+    rc = _load().oracle_certify_fps(pc.ctypes.data, pc.shape[0], pc.shape[1], picks.size, picks.ctypes.data,
+                                    n_forced, 0, n_threads or os.cpu_count() or 1, ctypes.addressof(bad))
+    if rc not in (0, 1):
+        raise RuntimeError(f"oracle_certify_fps failed with error code {rc}")
+    return rc == 0, int(bad.value)
+
+
+def certify_kdline(pc, picks, h, start=0, n_threads=None):
+    """True iff `picks` is what bucket_fps_kdline_sampling(pc, len(picks), h, start) yields: builds the
+    oracle permutation, maps the picks to positions and certifies exact FPS over the permuted rows."""
+    pc = _f32(pc)
+    perm, _, _ = kdline_build(pc, h)
+    inv = np.empty(perm.size, dtype=np.uint64)
+    inv[perm] = np.arange(perm.size, dtype=np.uint64)
+    picks = np.ascontiguousarray(picks, dtype=np.uint64)
+    if picks.size and (picks.max() >= perm.size or inv[picks[0]] != start):
+        return False, 0
+    pos = np.ascontiguousarray(inv[picks])
+    q = np.ascontiguousarray(pc[perm])
+    bad = ctypes.c_size_t(0)
+    rc = _load().oracle_certify_fps(q.ctypes.data, q.shape[0], q.shape[1], pos.size, pos.ctypes.data, 1, 1,
+                                    n_threads or os.cpu_count() or 1, ctypes.addressof(bad))
+    if rc not in (0, 1):
+        raise RuntimeError(f"oracle_certify_fps failed with error code {rc}")
+    return rc == 0, int(bad.value)
 
 
 def load_reference():

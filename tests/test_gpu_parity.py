@@ -1,0 +1,277 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI (include/fps_b200.h), against
+ (1) the committed golden vectors = outputs of the unmodified compiled reference,
+ (2) the CPU oracle on the same seeded inputs (bit-exact: indices are integers),
+ (3) at BASELINE.json's full sizes, the oracle where it finishes in seconds (its lazy kd-line form does)
+     and otherwise the multi-threaded certifier (oracle_certify_fps) on a seeded subset of clouds plus
+     size-independent properties on every cloud (range, first pick, distinctness, batch == single).
+Nothing here reads /root/reference.
+"""
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+from cases import CASES, input_sha, make_input  # noqa: E402
+
+import fpsample_b200 as fps  # noqa: E402
+from fpsample_b200 import capi, synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if capi.device_count() < 1:
+        pytest.fail("no sm_100 device visible: the CUDA path cannot run and there is no CPU fallback")
+
+
+def gpu_call(pc, call, p):
+    if call == "vanilla":
+        return capi.vanilla(pc, p["k"], p["start"])
+    return capi.kdline(pc, p["k"], p["h"], p["start"])
+
+
+# ---- (1) golden vectors ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_cuda_matches_reference_golden(case, golden):
+    cid, spec, call, p = case
+    pc = make_input(spec)
+    assert input_sha(pc) == str(golden[cid + "__in"])
+    before = capi.kernel_launches()
+    got = gpu_call(pc, call, p)
+    assert capi.kernel_launches() > before, "no CUDA kernel was launched"
+    assert got.dtype == np.uint64 and got.shape == (p["k"],)
+    np.testing.assert_array_equal(got, golden[cid].astype(np.uint64))
+
+
+def test_python_api_is_a_drop_in(golden):
+    """fpsample_b200.fps_sampling / bucket_fps_kdline_sampling: same call, same dtype, same indices."""
+    np.random.seed(42)
+    pc = np.random.rand(4096, 3)  # float64 in, like bench/test_bench.py:19-21
+    out = fps.fps_sampling(pc, 1024, start_idx=0)
+    assert out.dtype == np.uint64 and out.shape == (1024,)
+    np.testing.assert_array_equal(out, golden["G0_vanilla"])
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling(pc, 1024, 5, start_idx=0), golden["G0_kd_h5"])
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling(pc, 1024, h=7, start_idx=0), golden["G0_kd_h7"])
+    np.testing.assert_array_equal(fps.fps_sampling(np.asfortranarray(pc), 1024, 0), golden["G0_vanilla"])
+    ms = fps.fps_sampling(synth.uniform(77, 4096, 3), 256, [1, 2, 50, 4000])
+    np.testing.assert_array_equal(ms, golden["multi_start"])
+    np.random.seed(7)                      # random start honours np.random.seed (README.md:89-92)
+    a = fps.fps_sampling(pc, 16)
+    np.random.seed(7)
+    s = np.random.randint(0, 4096)
+    assert a[0] == s
+
+
+# ---- (2) oracle on seeded inputs: shapes that exercise every kernel plan -----------------------------------
+VANILLA_SHAPES = [  # n, d, k, start
+    (1, 3, 1, 0), (2, 3, 2, 1), (33, 3, 33, 5), (1000, 3, 100, 7), (4096, 6, 512, 5), (5000, 2, 300, 1),
+    (3000, 8, 200, 0), (16384, 3, 1024, 3), (777, 1, 200, 4), (2048, 5, 100, 9), (1500, 7, 100, 9),
+    (40000, 3, 300, 11), (3000, 12, 100, 2), (100000, 3, 500, 0), (100000, 6, 300, 0), (300000, 3, 200, 0),
+    (250000, 8, 64, 1), (1 << 20, 3, 64, 12345),
+]
+
+
+@pytest.mark.parametrize("n,d,k,s", VANILLA_SHAPES)
+def test_vanilla_vs_oracle(n, d, k, s, oracle):
+    pc = synth.uniform(n + d, n, d)
+    got = capi.vanilla(pc, k, s)
+    np.testing.assert_array_equal(got, oracle.fps_vanilla(pc, k, s), err_msg=capi.last_plan())
+
+
+KD_SHAPES = [  # n, d, k, h, start
+    (2, 3, 2, 1, 0), (64, 3, 20, 2, 1), (64, 3, 64, 6, 63), (1000, 3, 100, 3, 7), (4096, 3, 1024, 7, 3),
+    (4096, 6, 512, 5, 5), (5000, 2, 300, 4, 1), (3000, 8, 200, 6, 0), (777, 1, 200, 3, 4), (4096, 3, 200, 12, 0),
+    (50000, 3, 4096, 7, 0), (100000, 3, 2000, 9, 0), (100000, 6, 1000, 9, 0), (300000, 4, 1000, 8, 9),
+]
+
+
+@pytest.mark.parametrize("n,d,k,h,s", KD_SHAPES)
+def test_kdline_vs_oracle(n, d, k, h, s, oracle):
+    pc = synth.uniform(n + d + h, n, d)
+    got = capi.kdline(pc, k, h, s)
+    np.testing.assert_array_equal(got, oracle.kdline(pc, k, h, s), err_msg=capi.last_plan())
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_tie_clouds(seed, oracle):
+    """integer lattices: every tie rule and degenerate-split clamp (KDTreeBase.h:142-146)."""
+    d = (1, 2, 3, 6)[seed]
+    g = synth.grid_ties(seed, 3000, d, levels=4 + seed)
+    np.testing.assert_array_equal(capi.vanilla(g, 700, [5, 1, 9]), oracle.fps_vanilla(g, 700, [5, 1, 9]))
+    np.testing.assert_array_equal(capi.vanilla(g, 3000, 0), oracle.fps_vanilla(g, 3000, 0))
+    for h in (1, 4, 8, 11):
+        np.testing.assert_array_equal(capi.kdline(g, 700, h, seed), oracle.kdline(g, 700, h, seed), err_msg=f"h={h}")
+
+
+def test_unaligned_and_strided_inputs(oracle):
+    buf = synth.uniform(3, 4097 * 3 + 1, 1).ravel()
+    pc = buf[1:1 + 4097 * 3].reshape(4097, 3)           # base address 4 bytes off any 16-byte boundary
+    assert pc.ctypes.data % 16 != 0 or (pc.ctypes.data + 4) % 16 != 0
+    np.testing.assert_array_equal(capi.vanilla(pc, 500, 0), oracle.fps_vanilla(pc, 500, 0))
+    np.testing.assert_array_equal(capi.kdline(pc, 500, 5, 0), oracle.kdline(pc, 500, 5, 0))
+    wide = synth.uniform(4, 3000, 8)
+    view = wide[:, 2:5]                                  # non-contiguous view: the front-end copies (forcecast)
+    np.testing.assert_array_equal(fps.fps_sampling(view, 300, 1), oracle.fps_vanilla(np.ascontiguousarray(view), 300, 1))
+
+
+def test_kdline_build_matches_oracle(oracle):
+    """perm / leaf ranges / tight boxes of the GPU build == the oracle's."""
+    import torch
+    for (n, d, h, gen) in [(4096, 3, 5, "u"), (20000, 3, 7, "l"), (3000, 6, 6, "g"), (100000, 3, 9, "u"), (64, 2, 6, "g")]:
+        pc = {"u": lambda: synth.uniform(n, n, d), "l": lambda: synth.lidar(n, n),
+              "g": lambda: synth.grid_ties(n, n, d)}[gen]()
+        S = 1 << h
+        dp = torch.from_numpy(pc).cuda()
+        perm = torch.empty(n, dtype=torch.int32, device="cuda")
+        lo = torch.empty(S + 1, dtype=torch.int32, device="cuda")
+        box = torch.empty(S * 2 * d, dtype=torch.float32, device="cuda")
+        wsb = capi.workspace_bytes(capi.ALGO_KDLINE, 1, n, d, 1, h)
+        ws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda")
+        wp = (ws.data_ptr() + 255) & ~255
+        capi.kdline_build_dev(dp.data_ptr(), 1, n, d, h, perm.data_ptr(), lo.data_ptr(), box.data_ptr(), wp, wsb,
+                              torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        operm, obounds, obox = oracle.kdline_build(pc, h)
+        np.testing.assert_array_equal(perm.cpu().numpy().astype(np.uint64), operm)
+        glo = lo.cpu().numpy().astype(np.int64)
+        gbox = box.cpu().numpy().reshape(S, 2, d)
+        keep = np.flatnonzero(np.diff(glo) > 0)          # empty slots are allowed (early 'count==1' leaves)
+        np.testing.assert_array_equal(glo[keep], obounds[:-1].astype(np.int64))
+        assert glo[-1] == n
+        np.testing.assert_array_equal(gbox[keep], obox)
+
+
+def test_device_pointer_entries(oracle):
+    import torch
+    B, n, d, k, h = 6, 5000, 3, 400, 5
+    pcs = synth.uniform_batch(70, B, n, d)
+    dp = torch.from_numpy(pcs).cuda()
+    st = torch.arange(B, dtype=torch.int64, device="cuda")
+    out = torch.empty((B, k), dtype=torch.int64, device="cuda")
+    stream = torch.cuda.Stream()
+    for algo in (capi.ALGO_VANILLA, capi.ALGO_KDLINE):
+        wsb = capi.workspace_bytes(algo, B, n, d, k, h)
+        ws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda")
+        wp = (ws.data_ptr() + 255) & ~255
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            if algo == capi.ALGO_VANILLA:
+                capi.vanilla_batch_dev(dp.data_ptr(), B, n, d, k, st.data_ptr(), out.data_ptr(), wp, wsb, stream.cuda_stream)
+            else:
+                capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, st.data_ptr(), h, out.data_ptr(), wp, wsb, stream.cuda_stream)
+        stream.synchronize()
+        got = out.cpu().numpy().astype(np.uint64)
+        fn = (lambda b: oracle.fps_vanilla(pcs[b], k, b)) if algo == capi.ALGO_VANILLA else (lambda b: oracle.kdline(pcs[b], k, h, b))
+        np.testing.assert_array_equal(got, np.stack([fn(b) for b in range(B)]))
+    with pytest.raises(capi.FpsError) as e:               # too-small workspace is refused, not overrun
+        capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, out.data_ptr(), wp, 16, 0)
+    assert e.value.rc == 5
+
+
+def test_concurrent_callers(oracle):
+    """the module advertises free-threading (src/lib.cpp:581): concurrent calls must not interfere."""
+    pcs = [synth.uniform(900 + i, 3000 + 17 * i, 3) for i in range(8)]
+    res = [None] * 8
+
+    def work(i):
+        res[i] = (fps.fps_sampling(pcs[i], 300, i), fps.bucket_fps_kdline_sampling(pcs[i], 300, 4, i))
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(8)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for i in range(8):
+        np.testing.assert_array_equal(res[i][0], oracle.fps_vanilla(pcs[i], 300, i))
+        np.testing.assert_array_equal(res[i][1], oracle.kdline(pcs[i], 300, 4, i))
+
+
+# ---- (3) BASELINE.json configs at full size ---------------------------------------------------------------
+def test_cfg1_vanilla_4096(oracle):
+    pc = synth.uniform(1, 4096, 3)
+    np.testing.assert_array_equal(capi.vanilla(pc, 1024, 0), oracle.fps_vanilla(pc, 1024, 0))
+
+
+def test_cfg2_batch_1024x4096_h5(oracle):
+    pcs = synth.uniform_batch(1000, 1024, 4096, 3)
+    got = capi.kdline_batch(pcs, 1024, 5)
+    assert got.shape == (1024, 1024) and got.dtype == np.uint64
+    want = np.stack([oracle.kdline(pcs[b], 1024, 5, 0) for b in range(1024)])
+    np.testing.assert_array_equal(got, want)
+    # "indices checked bit-exact vs vanilla" (cfg 2) can only mean: exact FPS over the permuted array from
+    # position 0.  Without float ties that IS vanilla started at the same point:
+    van = capi.vanilla_batch(pcs, 1024, got[:, 0].copy())
+    same = (van == got).all(axis=1)
+    assert same.mean() > 0.95                             # the ~1.5 % that differ are exact float ties (F5)
+    for b in np.flatnonzero(~same)[:8]:
+        assert oracle.certify_vanilla(pcs[b], van[b])[0]  # vanilla's own tie rule holds on those
+    sub = np.arange(0, 1024, 64)
+    np.testing.assert_array_equal(van[sub], np.stack([oracle.fps_vanilla(pcs[b], 1024, int(got[b, 0])) for b in sub]))
+
+
+def test_cfg3_batch_64x16384_h7(oracle):
+    pcs = synth.uniform_batch(2000, 64, 16384, 3)
+    got = capi.kdline_batch(pcs, 4096, 7)
+    np.testing.assert_array_equal(got, np.stack([oracle.kdline(pcs[b], 4096, 7, 0) for b in range(64)]))
+    van = capi.vanilla_batch(pcs, 4096)
+    for b in range(0, 64, 8):
+        assert oracle.certify_vanilla(pcs[b], van[b])[0], b
+    assert (van[:, 0] == 0).all()
+
+
+@pytest.mark.parametrize("gen", ["uniform", "lidar"])
+def test_cfg4_single_1m_to_64k_h9(gen, oracle, golden):
+    pc = synth.uniform(5, 2**20, 3) if gen == "uniform" else synth.lidar(6, 2**20)
+    got = capi.kdline(pc, 65536, 9, 0)
+    np.testing.assert_array_equal(got, golden["G5_kd_h9" if gen == "uniform" else "G6_kd_h9"])
+    assert len(np.unique(got)) == 65536
+
+
+def test_cfg4_vanilla_1m_certified(oracle):
+    """vanilla at 2^20 points: the sequential oracle needs minutes, the threaded certifier seconds."""
+    pc = synth.uniform(5, 2**20, 3)
+    k = 8192
+    got = capi.vanilla(pc, k, 0)
+    ok, where = oracle.certify_vanilla(pc, got)
+    assert ok, f"first bad round {where} ({capi.last_plan()})"
+
+
+@pytest.mark.parametrize("d", [3, 6])
+def test_cfg5_batch_100k_to_8192(d, oracle, golden):
+    """full single-cloud size, a 64-cloud slice of the 4096-cloud batch (the full batch is bench.py's job);
+    kd-line h=7 against the oracle for every cloud, vanilla certified on a subset."""
+    B = 64
+    pcs = synth.uniform_batch(3000, B, 100000, d)
+    got = capi.kdline_batch(pcs, 8192, 7)
+    np.testing.assert_array_equal(got[0], golden["cfg5_b0_d3_kd" if d == 3 else "cfg5_b0_d6_kd"])
+    for b in range(B):
+        assert len(np.unique(got[b])) == 8192 and got[b].max() < 100000
+    for b in range(0, B, 4 if d == 3 else 16):
+        np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], 8192, 7, 0), err_msg=f"cloud {b}")
+    van = capi.vanilla_batch(pcs[:16], 8192)
+    if d == 3:
+        np.testing.assert_array_equal(van[1], golden["cfg5_b1_d3_vanilla"])
+    for b in (0, 7, 15):
+        assert oracle.certify_vanilla(pcs[b], van[b])[0], b
+
+
+def test_batch_equals_single_and_per_cloud_starts(oracle):
+    pcs = synth.uniform_batch(4000, 37, 4096, 3)
+    st = np.arange(37) * 11
+    got = capi.vanilla_batch(pcs, 256, st)
+    np.testing.assert_array_equal(got, np.stack([capi.vanilla(pcs[b], 256, int(st[b])) for b in range(37)]))
+    np.testing.assert_array_equal(got, np.stack([oracle.fps_vanilla(pcs[b], 256, int(st[b])) for b in range(37)]))
+    gk = fps.bucket_fps_kdline_sampling_batch(pcs, 256, 5, start_idx=list(st))
+    np.testing.assert_array_equal(gk, np.stack([oracle.kdline(pcs[b], 256, 5, int(st[b])) for b in range(37)]))
+
+
+def test_multi_device_sharding_in_process(oracle):
+    nd = capi.device_count()
+    if nd < 2:
+        pytest.skip("one GPU visible")
+    pcs = synth.uniform_batch(5000, 4 * nd + 1, 4096, 3)
+    a = capi.kdline_batch(pcs, 512, 5, devices=list(range(nd)))
+    b = capi.kdline_batch(pcs, 512, 5, devices=[0])
+    np.testing.assert_array_equal(a, b)

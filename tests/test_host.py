@@ -1,0 +1,147 @@
+"""CPU suite: host-side logic and the drop-in boundary, no GPU compute.
+
+ - libfps_b200.so loads and exports every symbol include/fps_b200.h declares (and nothing undeclared);
+ - the python front-end mirrors the reference's argument / exception behaviour (src/fpsample/__init__.py,
+   src/lib.cpp:52-109, 249-270, 522-579) for everything that is decided before device work starts;
+ - without a GPU every compute entry fails LOUDLY (no CPU fallback), and the product never touches oracle/.
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import fpsample_b200 as fps
+from fpsample_b200 import capi, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAVE_GPU = capi.device_count() > 0
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "fps_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(r"FPS_API\s+[\w\s\*]+?\b(\w+)\s*\(", txt))
+
+
+def test_header_declares_expected_entry_points():
+    syms = header_symbols()
+    assert {"fps_b200_vanilla", "bucket_fps_kdline", "fps_b200_vanilla_batch", "fps_b200_kdline_batch"} <= syms
+    assert syms == set(capi.EXPORTS), "capi.py binding table and include/fps_b200.h disagree"
+
+
+def test_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(capi.LIB_PATH)
+    for s in header_symbols():
+        assert hasattr(L, s), f"{s} declared in include/fps_b200.h but not exported"
+    out = subprocess.check_output(["nm", "-D", "--defined-only", capi.LIB_PATH], text=True)
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    extra = {s for s in exported if not s.startswith("_")} - header_symbols()
+    assert not extra, f"undeclared exports: {extra}"
+
+
+def test_library_is_sm100a_only_and_torch_free():
+    out = subprocess.check_output(["cuobjdump", "-lelf", capi.LIB_PATH], text=True)
+    archs = set(re.findall(r"sm_\d+a?", out))
+    assert archs == {"sm_100a"}, archs
+    ldd = subprocess.check_output(["ldd", capi.LIB_PATH], text=True)
+    assert "torch" not in ldd and "python" not in ldd
+
+
+def test_version_strings():
+    assert b"sm_100a" in capi.lib().fps_b200_version()
+    assert fps.__version__.startswith("1.0.2")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "fpsample_b200")
+    for dp, _, fns in os.walk(pkg):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dp, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|oracle/|liboracle", src, flags=re.M), fn
+
+
+# ---- python front-end: reference behaviour decided before any device work ---------------------------------
+PC = synth.uniform(0, 100, 3)
+
+
+def test_assertions_like_reference():
+    with pytest.raises(AssertionError):
+        fps.fps_sampling(PC, 0, 0)                      # n_samples >= 1        (__init__.py:49)
+    with pytest.raises(AssertionError):
+        fps.fps_sampling(PC[0], 1, 0)                   # ndim == 2             (:50)
+    with pytest.raises(AssertionError):
+        fps.fps_sampling(PC, 101, 0)                    # n_pts >= n_samples    (:52)
+    with pytest.raises(AssertionError):
+        fps.fps_sampling(PC, 10, 100)                   # start range           (:53-56)
+    with pytest.raises(AssertionError):
+        fps.fps_sampling(PC, 2, [1, 2, 3])              # len(list) <= n_samples(:57-60)
+    with pytest.raises(AssertionError):
+        fps.bucket_fps_kdline_sampling(PC, 10, 0, 0)    # h >= 1                (:196)
+    with pytest.raises(AssertionError):
+        fps.bucket_fps_kdline_sampling(PC, 10, 7, 0)    # 2**h <= n_pts         (:197)
+    with pytest.raises(TypeError):
+        fps.bucket_fps_kdline_sampling(PC, 10, 3, [1, 2])  # list start dies in the range assert (:198-200)
+
+
+def test_start_idx_types_like_reference():
+    with pytest.raises(ValueError, match="start_idx should be None, int or list"):
+        fps.fps_sampling(PC, 10, np.int64(3))           # numpy scalar is rejected (__init__.py:30-31)
+    with pytest.raises(ValueError):
+        fps.fps_sampling(PC, 10, 3.0)
+
+
+def test_pybind_layer_errors_like_reference():
+    m = fps._fpsample
+    with pytest.raises(TypeError):
+        m._fps_sampling(PC, 10, "0")                    # lib.cpp:260
+    with pytest.raises(ValueError):
+        m._fps_sampling(PC, 101, 0)                     # lib.cpp:76-81
+    with pytest.raises(ValueError):
+        m._fps_sampling(PC, 10, 100)                    # lib.cpp:83-107
+    with pytest.raises(ValueError):
+        m._fps_sampling(PC, 2, np.array([1, 2, 3], dtype=np.uint64))
+    with pytest.raises(TypeError):
+        m._bucket_fps_kdline_sampling(PC, 10, 3, "0")   # lib.cpp:534
+    with pytest.raises(NotImplementedError):
+        m._bucket_fps_kdline_sampling(PC, 10, 3, np.array([1], dtype=np.uint64))  # lib.cpp:537-540
+    with pytest.raises(ValueError):
+        m._bucket_fps_kdline_sampling(PC, 10, 3, 100)   # lib.cpp:545-547
+    with pytest.raises(ValueError):
+        m._bucket_fps_kdline_sampling(PC, 0, 3, 0)      # lib.cpp:548-553
+    with pytest.raises(ValueError):
+        m._bucket_fps_kdline_sampling(PC, 10, 0, 0)     # lib.cpp:554-557
+
+
+def test_c_abi_return_codes_like_reference():
+    """src/wrapper.hpp:121-127: rc 1 bad dim before rc 2 bad start; both decided before device work."""
+    out = np.empty(4, dtype=np.uint64)
+    pc9 = synth.uniform(0, 50, 9)
+    L = capi.lib()
+    assert L.bucket_fps_kdline(pc9.ctypes.data, 50, 9, 4, 99, 2, out.ctypes.data) == 1
+    assert L.bucket_fps_kdline(PC.ctypes.data, 100, 3, 4, 100, 2, out.ctypes.data) == 2
+    assert b"start_idx" in L.fps_b200_last_error()
+    assert L.bucket_fps_kdline(PC.ctypes.data, 100, 3, 0, 0, 2, out.ctypes.data) == 3
+    st = np.array([100], dtype=np.uint64)
+    assert L.fps_b200_vanilla(PC.ctypes.data, 100, 3, 4, st.ctypes.data, 1, out.ctypes.data) == 2
+    with pytest.raises(RuntimeError, match="failed with error code 1"):  # lib.cpp:574-576
+        fps._fpsample._bucket_fps_kdline_sampling(pc9, 4, 2, 0)
+
+
+def test_out_of_scope_entries_say_so():
+    for f in (fps.fps_npdu_sampling, fps.fps_npdu_kdtree_sampling, fps.bucket_fps_kdtree_sampling):
+        with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
+            f(PC, 10)
+
+
+@pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback_without_gpu():
+    assert capi.device_count() == 0
+    for call in (lambda: fps.fps_sampling(PC, 10, 0), lambda: fps.bucket_fps_kdline_sampling(PC, 10, 3, 0),
+                 lambda: fps.fps_sampling_batch(PC[None], 10), lambda: fps.bucket_fps_kdline_sampling_batch(PC[None], 10, 3)):
+        with pytest.raises(RuntimeError, match="error code 4"):   # FPS_ERR_NO_DEVICE
+            call()
+    assert "no CPU fallback" in capi.lib().fps_b200_last_error().decode()
