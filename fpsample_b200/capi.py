@@ -28,6 +28,7 @@ EXPORTS = {
     "fps_b200_last_error": (ctypes.c_char_p, []),
     "fps_b200_last_plan": (ctypes.c_char_p, []),
     "fps_b200_kernel_launches": (ctypes.c_uint64, []),
+    "fps_b200_debug_counters": (ctypes.c_int, [ctypes.c_void_p]),
     "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fps_b200_host_free": (None, [ctypes.c_void_p]),
 }
@@ -67,6 +68,15 @@ def last_plan() -> str:
 
 def kernel_launches() -> int:
     return int(lib().fps_b200_kernel_launches())
+
+
+def debug_counters():
+    """phase counters of the last kd-line cluster launch: dict (diagnostics only)."""
+    out = np.zeros(16, dtype=np.uint64)
+    _check("fps_b200_debug_counters", lib().fps_b200_debug_counters(out.ctypes.data))
+    names = ("iterations", "picks", "stalled_iterations", "cyc_poll_warptop", "cyc_wait_warps", "cyc_blocktop",
+             "cyc_tests")
+    return {k: int(v) for k, v in zip(names, out)}
 
 
 def device_count() -> int:

@@ -213,13 +213,37 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
     return FPS_OK;
 }
 
+struct KdLayout {
+    KdlinePlan pl;
+    AsyncPlan ap;
+    bool async;
+    size_t region_off, region_stride, total;
+};
+
+// fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
+// and sample with the cluster coordinator/worker kernel
+static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L) {
+    cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
+    if (e != cudaSuccess) return e;
+    L->async = !build_only && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
+    L->region_off = L->region_stride = 0;
+    L->total = L->pl.ws_bytes;
+    if (L->async) {
+        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        L->region_stride = kd_region_bytes(n, dim, h);
+        L->total = L->region_off + B * L->region_stride;
+    }
+    return cudaSuccess;
+}
+
 static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts, size_t h,
                           u64 *d_out, u32 *perm_out, u32 *leaf_lo_out, float *leaf_box_out, void *ws,
                           size_t ws_bytes, int n_sms, cudaStream_t st) {
-    KdlinePlan pl;
-    CK(plan_kdline(n, dim, h, B, n_sms, &pl));
-    if (!ws || ws_bytes < pl.ws_bytes || (reinterpret_cast<uintptr_t>(ws) & 255)) {
-        set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", pl.ws_bytes, ws_bytes);
+    KdLayout L;
+    CK(kd_layout(B, n, dim, h, n_sms, d_out == nullptr, &L));
+    const KdlinePlan &pl = L.pl;
+    if (!ws || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", L.total, ws_bytes);
         return FPS_ERR_WORKSPACE;
     }
     KdlineArgs a;
@@ -235,6 +259,18 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     a.dim = (u32)dim;
     a.k = (u32)k;
     a.h = (u32)h;
+    if (L.async) {
+        a.region = static_cast<unsigned char *>(ws) + L.region_off;
+        a.region_stride = L.region_stride;
+        set_plan("kdline_kernel<DIM=%d>(build) grid=%u threads=%u + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
+                 "cluster=%u threads=%u smem=%zu R=%u region/cloud=%zu",
+                 pl.dimp, pl.grid, pl.threads, L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
+                 L.region_stride);
+        CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        CK(launch_kdline_async(L.ap, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k,
+                               (u32)h, st));
+        return FPS_OK;
+    }
     set_plan("kdline_kernel<DIM=%d> clouds=%zu grid=%u threads=%u smem=%zu placement=%s ws/cta=%zu", pl.dimp, B, pl.grid,
              pl.threads, pl.smem, pl.in_smem == 3 ? "smem" : (pl.in_smem == 2 ? "meta-smem,data-L2" : "L2"),
              pl.ws_stride);
@@ -278,9 +314,9 @@ static int run_shard(int dev, const ShardJob &j) {
             vanilla_layout(nb, j.n, j.dim, cx->n_sms, &L);
             ws_need = L.total;
         } else {
-            KdlinePlan pl;
-            CK(plan_kdline(j.n, j.dim, j.h, nb, cx->n_sms, &pl));
-            ws_need = pl.ws_bytes;
+            KdLayout L;
+            CK(kd_layout(nb, j.n, j.dim, j.h, cx->n_sms, false, &L));
+            ws_need = L.total;
         }
         if ((rc = ln.in.ensure(nb * in_per)) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) break;
         u64 *d_starts = nullptr;
@@ -376,6 +412,13 @@ const char *fps_b200_last_error(void) { return tl_err; }
 const char *fps_b200_last_plan(void) { return tl_plan; }
 uint64_t fps_b200_kernel_launches(void) { return g_launches.load(); }
 
+int fps_b200_debug_counters(uint64_t *out16) {
+    if (!out16) return FPS_ERR_ARG;
+    CK(cudaDeviceSynchronize());
+    CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
+    return FPS_OK;
+}
+
 void *fps_b200_host_alloc(size_t bytes) {
     void *p = nullptr;
     if (cudaMallocHost(&p, bytes) != cudaSuccess) {
@@ -466,12 +509,12 @@ size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t
         return L.total;
     }
     if (dim > FPS_B200_MAX_KDLINE_DIM || check_kdline(n, dim, height)) return 0;
-    KdlinePlan pl;
-    if (plan_kdline(n, dim, height, B, n_sms, &pl) != cudaSuccess) {
+    KdLayout L;
+    if (kd_layout(B, n, dim, height, n_sms, false, &L) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
-    return pl.ws_bytes;
+    return L.total;
 }
 
 int fps_b200_vanilla_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k,

@@ -57,6 +57,8 @@ struct KdlineArgs {
     u32 *perm_out;      // [B][n]
     u32 *leaf_lo_out;   // [B][2^h+1]
     float *leaf_box_out;// [B][2^h][2][dim]
+    unsigned char *region;  // build-only into per-cloud regions (see kd_region_bytes), nullptr = fused build+sample
+    size_t region_stride;
     u32 B, n, dim, k, h;
     u32 in_smem;        // bit0: coordinates + scratch in shared memory, bit1: node/bucket metadata in shared memory
 };
@@ -71,6 +73,20 @@ struct KdlinePlan {
 
 cudaError_t plan_kdline(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdlinePlan *pl);
 cudaError_t launch_kdline(const KdlinePlan &pl, KdlineArgs a, unsigned char *ws_base, cudaStream_t st);
+
+// ---- kd-line, asynchronous coordinator/worker sampling over prebuilt regions (kdline_async.cu) -----------
+// per-cloud region: [q dim*npad f32][dis npad f32][perm npad u32][nlo pad32(S+1) u32][fbox S*2*dim f32]
+size_t kd_region_bytes(size_t n, size_t dim, size_t h);
+struct AsyncPlan {
+    int dimp;
+    u32 C, threads, R, clusters;
+    size_t smem;
+};
+bool plan_kdline_async(size_t n, size_t dim, size_t h, size_t B, int n_sms, AsyncPlan *pl);
+cudaError_t launch_kdline_async(const AsyncPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts,
+                                u64 *out, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
+
+cudaError_t async_debug_counters(u64 *out16);
 
 void count_launch();
 

@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
         data_base = sm;
         sm += (data_bytes + 15) & ~(size_t)15;
     } else {
-        data_base = gw;
-        gw += (data_bytes + 15) & ~(size_t)15;
+        data_base = gw;   // replaced per cloud when a.region is set
+        if (!a.region) gw += (data_bytes + 15) & ~(size_t)15;
     }
     meta_base = (a.in_smem & 2) ? sm : gw;
     (void)meta_bytes;
@@ -155,6 +155,16 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
 
         const float *gcloud = a.pts + (size_t)cloud * n * dim;
         u32 *perm = a.perm_out ? a.perm_out + (size_t)cloud * n : perm_ws;
+        u32 *r_nlo = nullptr;
+        float *r_box = nullptr;
+        if (a.region) {  // build-only into the per-cloud region: [q dim*npad][dis npad][perm npad][nlo][fbox]
+            unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
+            q = reinterpret_cast<float *>(rg);
+            scr = reinterpret_cast<u32 *>(rg) + (size_t)dim * npad;
+            perm = scr + npad;
+            r_nlo = perm + npad;
+            r_box = reinterpret_cast<float *>(r_nlo + ((S + 1 + 31) & ~31u));
+        }
 
         // ---- stage: row-major -> SoA, identity permutation ---------------------------------------------
         for (u32 f = tid; f < n * dim; f += T) {
@@ -319,7 +329,11 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
             for (u32 s = tid; s <= S; s += T) a.leaf_lo_out[(size_t)cloud * (S + 1) + s] = nlo[s];
         if (a.leaf_box_out)
             for (u32 e = tid; e < S * 2 * dim; e += T) a.leaf_box_out[(size_t)cloud * S * 2 * dim + e] = fbox[e];
-        if (!a.out) continue;
+        if (r_nlo) {
+            for (u32 s = tid; s <= S; s += T) r_nlo[s] = nlo[s];
+            for (u32 e = tid; e < S * 2 * dim; e += T) r_box[e] = fbox[e];
+        }
+        if (!a.out || a.region) continue;
 
         // ---- sample -------------------------------------------------------------------------------------
         float *dis = reinterpret_cast<float *>(scr);

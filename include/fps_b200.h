@@ -99,6 +99,7 @@ FPS_API const char *fps_b200_version(void);
 FPS_API const char *fps_b200_last_error(void);      /* thread-local description of the last failure           */
 FPS_API uint64_t fps_b200_kernel_launches(void);    /* kernels launched by this library in this process       */
 FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kernel/shape the last call picked  */
+FPS_API int fps_b200_debug_counters(uint64_t *out16); /* phase counters of the last kd-line cluster launch (diagnostics) */
 FPS_API void *fps_b200_host_alloc(size_t bytes);    /* page-locked host memory for the host-pointer entries   */
 FPS_API void fps_b200_host_free(void *p);
 

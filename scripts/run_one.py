@@ -1,0 +1,32 @@
+"""Run one workload a few times through the device-pointer C ABI (for ncu launch lists / quick timings).
+usage: python scripts/run_one.py <workload> <algo> [reps] [B override]"""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from fpsample_b200 import capi
+
+wl, algo = sys.argv[1], sys.argv[2]
+reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+B, n, d, k, h, gen, seed, desc = bench.WORKLOADS[wl]
+if len(sys.argv) > 4: B = int(sys.argv[4])
+host = np.stack([bench.make_cloud(gen, seed + b, n, d) for b in range(B)])
+dp = torch.from_numpy(host).cuda()
+do = torch.empty((B, k), dtype=torch.int64, device="cuda")
+a = capi.ALGO_VANILLA if algo == "vanilla" else capi.ALGO_KDLINE
+wsb = capi.workspace_bytes(a, B, n, d, k, h)
+ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda")
+wp = (ws.data_ptr() + 255) & ~255
+st = torch.cuda.current_stream()
+def fn():
+    if algo == "vanilla": capi.vanilla_batch_dev(dp.data_ptr(), B, n, d, k, 0, do.data_ptr(), wp, wsb, st.cuda_stream)
+    else: capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, do.data_ptr(), wp, wsb, st.cuda_stream)
+fn(); torch.cuda.synchronize()
+ts = []
+for _ in range(reps):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print(f"{wl} {algo} B={B}: min {min(ts):.3f} ms mean {sum(ts)/len(ts):.3f} ms -> {B/min(ts)*1e3:.1f} clouds/s | {capi.last_plan()}")
+if algo == "kdline" and "async" in capi.last_plan():
+    d = capi.debug_counters(); it = max(d["iterations"], 1)
+    print("  dbg:", d, "| per iteration:", {k: round(v / it, 1) for k, v in d.items() if k.startswith("cyc")}, "picks/iter %.2f" % (d["picks"] / it))

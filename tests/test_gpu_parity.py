@@ -107,6 +107,27 @@ def test_tie_clouds(seed, oracle):
         np.testing.assert_array_equal(capi.kdline(g, 700, h, seed), oracle.kdline(g, 700, h, seed), err_msg=f"h={h}")
 
 
+@pytest.mark.parametrize("n,d,levels,k,h,s", [(60000, 3, 24, 3000, 6, 5), (40000, 2, 40, 2500, 8, 0), (30000, 6, 3, 1500, 7, 9),
+                                              (70000, 1, 5000, 2000, 5, 1), (20000, 3, 2, 500, 10, 0)])
+def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle):
+    """clouds too big for one SM go through the coordinator/worker cluster kernel: ties, duplicates and
+    near-empty buckets must not disturb its upper-bound logic."""
+    g = synth.grid_ties(n + h, n, d, levels=levels)
+    got = capi.kdline(g, k, h, s)
+    assert "kdline_async_kernel" in capi.last_plan()
+    np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
+
+
+def test_async_batches_and_cluster_sizes(oracle):
+    for B, n, k, h in [(3, 30000, 800, 7), (20, 20000, 400, 6), (80, 16384, 300, 7), (160, 14000, 200, 5)]:
+        pcs = synth.uniform_batch(8000 + B, B, n, 3)
+        st = (np.arange(B) * 7) % n
+        got = capi.kdline_batch(pcs, k, h, st, devices=[0])
+        assert "kdline_async_kernel" in capi.last_plan(), capi.last_plan()
+        want = np.stack([oracle.kdline(pcs[b], k, h, int(st[b])) for b in range(B)])
+        np.testing.assert_array_equal(got, want, err_msg=capi.last_plan())
+
+
 def test_unaligned_and_strided_inputs(oracle):
     buf = synth.uniform(3, 4097 * 3 + 1, 1).ravel()
     pc = buf[1:1 + 4097 * 3].reshape(4097, 3)           # base address 4 bytes off any 16-byte boundary
