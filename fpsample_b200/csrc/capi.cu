@@ -3,6 +3,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -216,8 +217,8 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
 struct KdLayout {
     KdlinePlan pl;
     AsyncPlan ap;
-    bool async;
-    size_t region_off, region_stride, total;
+    bool async, gridbuild;
+    size_t region_off, region_stride, aux_off, total;
 };
 
 // fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
@@ -226,12 +227,17 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
     L->async = !build_only && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
-    L->region_off = L->region_stride = 0;
+    L->region_off = L->region_stride = L->aux_off = 0;
+    L->gridbuild = false;
     L->total = L->pl.ws_bytes;
     if (L->async) {
+        // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
+        L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
+        if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
         L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
         L->region_stride = kd_region_bytes(n, dim, h);
-        L->total = L->region_off + B * L->region_stride;
+        L->aux_off = L->region_off + B * L->region_stride;
+        L->total = L->aux_off + (L->gridbuild ? B * kd_gridbuild_aux_bytes(n, dim, h) : 0);
     }
     return cudaSuccess;
 }
@@ -262,11 +268,15 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     if (L.async) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
-        set_plan("kdline_kernel<DIM=%d>(build) grid=%u threads=%u + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
+        set_plan("%s + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
                  "cluster=%u threads=%u smem=%zu R=%u region/cloud=%zu",
-                 pl.dimp, pl.grid, pl.threads, L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
+                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
                  L.region_stride);
-        CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (L.gridbuild)
+            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
+                                   (u32)n, (u32)dim, (u32)h, st));
+        else
+            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
         CK(launch_kdline_async(L.ap, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k,
                                (u32)h, st));
         return FPS_OK;

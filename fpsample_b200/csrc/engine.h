@@ -88,6 +88,11 @@ cudaError_t launch_kdline_async(const AsyncPlan &pl, unsigned char *region, size
 
 cudaError_t async_debug_counters(u64 *out16);
 
+// ---- kd-line build with the whole grid per level (kdbuild.cu), into the same per-cloud regions -------------
+size_t kd_gridbuild_aux_bytes(size_t n, size_t dim, size_t h);
+cudaError_t launch_kd_gridbuild(const float *pts, unsigned char *region, size_t region_stride, unsigned char *aux,
+                                u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
+
 void count_launch();
 
 }  // namespace fps

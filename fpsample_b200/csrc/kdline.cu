@@ -22,6 +22,7 @@
 
 #include "common.cuh"
 #include "engine.h"
+#include "kdcommon.cuh"
 
 namespace fps {
 
@@ -29,82 +30,6 @@ struct KdFixedSmem {
     u64 wslot[2][32];
     u32 cloud;
 };
-
-__device__ __forceinline__ u32 roundup32(u32 x) { return (x + 31u) & ~31u; }
-
-// tight boxes of [s0,s1) split at sp: positions < sp go to boxL, the rest to boxR (ordered ints)
-template <int DIM>
-__device__ __forceinline__ void box_range(const float *q, u32 npad, u32 dim, u32 s0, u32 s1, u32 sp,
-                                          int *boxL, int *boxR) {
-    const u32 lane = lane_id();
-    int lmin[DIM], lmax[DIM], rmin[DIM], rmax[DIM];
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        lmin[c] = rmin[c] = 0x7fffffff;
-        lmax[c] = rmax[c] = (int)0x80000000;
-    }
-    for (u32 i = s0 + lane; i < s1; i += 32) {
-        const bool left = i < sp;
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) {
-            if (c < (int)dim) {
-                int o = f2ord(q[(size_t)c * npad + i]);
-                if (left) {
-                    lmin[c] = min(lmin[c], o);
-                    lmax[c] = max(lmax[c], o);
-                } else {
-                    rmin[c] = min(rmin[c], o);
-                    rmax[c] = max(rmax[c], o);
-                }
-            }
-        }
-    }
-    const bool anyL = s0 < min(s1, sp), anyR = max(s0, sp) < s1;
-#pragma unroll
-    for (int c = 0; c < DIM; ++c) {
-        if (c < (int)dim) {
-            if (anyL) {
-                int a = __reduce_min_sync(FULL, lmin[c]), b = __reduce_max_sync(FULL, lmax[c]);
-                if (lane == 0) {
-                    atomicMin(boxL + c, a);
-                    atomicMax(boxL + dim + c, b);
-                }
-            }
-            if (anyR) {
-                int a = __reduce_min_sync(FULL, rmin[c]), b = __reduce_max_sync(FULL, rmax[c]);
-                if (lane == 0) {
-                    atomicMin(boxR + c, a);
-                    atomicMax(boxR + dim + c, b);
-                }
-            }
-        }
-    }
-}
-
-// strictly sequential binary32 sum of src[0..count) in order, computed redundantly by all 32 lanes:
-// lanes fetch 32 consecutive values, then the chain consumes them through shuffles.
-__device__ __forceinline__ float seq_sum(const float *src, u32 count) {
-    const u32 lane = lane_id();
-    float sum = 0.0f;
-    u32 i = 0;
-    for (; i + 128 <= count; i += 128) {
-        float x0 = src[i + lane], x1 = src[i + 32 + lane], x2 = src[i + 64 + lane], x3 = src[i + 96 + lane];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x0, j));
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x1, j));
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x2, j));
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x3, j));
-    }
-    for (; i < count; i += 32) {
-        float x = (i + lane < count) ? src[i + lane] : 0.0f;
-        const u32 m = min(32u, count - i);
-        for (u32 j = 0; j < m; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x, j));
-    }
-    return sum;
-}
 
 template <int DIM>
 __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work_counter) {
@@ -121,7 +46,8 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
     // ---- carve memory: data = q[dim][npad] + scr[npad]; meta = nlo | box | 4 per-node arrays | part ---
     const size_t data_bytes = ((size_t)dim + 1) * npad * 4;
     const size_t meta_bytes = ((size_t)(S + 1) + (size_t)S * 2 * dim + 4 * (size_t)S + PN) * 4;
-    unsigned char *sm = smem_raw + ((sizeof(KdFixedSmem) + 15) & ~15);
+    float *chainbuf = reinterpret_cast<float *>(smem_raw + ((sizeof(KdFixedSmem) + 15) & ~15)) + (size_t)warp * 256;
+    unsigned char *sm = smem_raw + ((sizeof(KdFixedSmem) + 15) & ~15) + (size_t)NW * 1024;
     unsigned char *gw = a.ws + (size_t)blockIdx.x * a.ws_stride;
     u32 *perm_ws = reinterpret_cast<u32 *>(gw);
     gw += (size_t)npad * 4;
@@ -205,7 +131,7 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                             sd = c;
                         }
                     }
-                    float sum = seq_sum(q + (size_t)sd * npad + lo, hi - lo);
+                    float sum = seq_sum_staged(q + (size_t)sd * npad + lo, hi - lo, chainbuf);
                     float val = __fdiv_rn(sum, __uint2float_rn(hi - lo));
                     if (lane == 0) {
                         A0[j] = __float_as_uint(val);
@@ -446,7 +372,7 @@ cudaError_t plan_kdline(size_t n, size_t dim, size_t h, size_t B, int n_sms, Kdl
     u32 threads = n <= 8192 ? 256 : (n <= 65536 ? 512 : 1024);
     while (threads < 1024 && S > (size_t)threads) threads *= 2;  // at most ~32 buckets per warp
     const size_t NW = threads / 32;
-    const size_t fixed = (sizeof(KdFixedSmem) + 15) & ~(size_t)15;
+    const size_t fixed = ((sizeof(KdFixedSmem) + 15) & ~(size_t)15) + NW * 1024;  // + per-warp chain staging
     const size_t data = (((dim + 1) * npad * 4) + 15) & ~(size_t)15;
     const size_t meta = (kd_meta_bytes(S, dim, NW) + 15) & ~(size_t)15;
     const size_t cap = 200 * 1024;
