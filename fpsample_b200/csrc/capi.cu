@@ -217,8 +217,9 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
 struct KdLayout {
     KdlinePlan pl;
     AsyncPlan ap;
-    bool async, gridbuild;
-    size_t region_off, region_stride, aux_off, total;
+    WarpPlan wp;
+    bool async, gridbuild, warp;
+    size_t region_off, region_stride, aux_off, counter_off, total;
 };
 
 // fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
@@ -226,10 +227,20 @@ struct KdLayout {
 static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L) {
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
-    L->async = !build_only && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
-    L->region_off = L->region_stride = L->aux_off = 0;
+    L->region_off = L->region_stride = L->aux_off = L->counter_off = 0;
     L->gridbuild = false;
     L->total = L->pl.ws_bytes;
+    // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
+    L->warp = !build_only && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
+    if (L->warp) {
+        L->async = false;
+        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        L->region_stride = kd_region_bytes(n, dim, h);
+        L->counter_off = L->region_off + B * L->region_stride;
+        L->total = L->counter_off + 256;
+        return cudaSuccess;
+    }
+    L->async = !build_only && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
     if (L->async) {
         // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
         L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
@@ -265,6 +276,19 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     a.dim = (u32)dim;
     a.k = (u32)k;
     a.h = (u32)h;
+    if (L.warp) {
+        a.region = static_cast<unsigned char *>(ws) + L.region_off;
+        a.region_stride = L.region_stride;
+        set_plan("kdline_kernel(build, 1 CTA per cloud) + kdline_warp_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
+                 "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
+                 L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
+                 L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
+        CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
+                              reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
+                              (u32)dim, (u32)k, (u32)h, st));
+        return FPS_OK;
+    }
     if (L.async) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
@@ -425,7 +449,10 @@ uint64_t fps_b200_kernel_launches(void) { return g_launches.load(); }
 int fps_b200_debug_counters(uint64_t *out16) {
     if (!out16) return FPS_ERR_ARG;
     CK(cudaDeviceSynchronize());
-    CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
+    if (getenv("FPS_B200_DBG_WARP"))
+        CK(warp_debug_counters(reinterpret_cast<u64 *>(out16)));
+    else
+        CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
     return FPS_OK;
 }
 

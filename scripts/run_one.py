@@ -30,3 +30,9 @@ print(f"{wl} {algo} B={B}: min {min(ts):.3f} ms mean {sum(ts)/len(ts):.3f} ms ->
 if algo == "kdline" and "async" in capi.last_plan():
     d = capi.debug_counters(); it = max(d["iterations"], 1)
     print("  dbg:", d, "| per iteration:", {k: round(v / it, 1) for k, v in d.items() if k.startswith("cyc")}, "picks/iter %.2f" % (d["picks"] / it))
+if algo == "kdline" and "warp" in capi.last_plan():
+    os.environ["FPS_B200_DBG_WARP"] = "1"
+    out = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(out.ctypes.data)
+    it = max(int(out[0]), 1)
+    if int(out[0]): print("  warp dbg (cloud 0): picks %d | per pick: test %.0f scan %.0f reduce %.0f argmax %.0f total %.0f cyc | buckets/pick %.2f groups/pick %.2f" % (
+        out[0], out[1] / it, out[2] / it, out[3] / it, out[4] / it, out[7] / it, out[5] / it, out[6] / it))
