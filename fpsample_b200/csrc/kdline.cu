@@ -83,13 +83,21 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
         u32 *perm = a.perm_out ? a.perm_out + (size_t)cloud * n : perm_ws;
         u32 *r_nlo = nullptr;
         float *r_box = nullptr;
+        float *r_q = nullptr;
+        u32 *r_perm = nullptr;
         if (a.region) {  // build-only into the per-cloud region: [q dim*npad][dis npad][perm npad][nlo][fbox]
             unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
-            q = reinterpret_cast<float *>(rg);
-            scr = reinterpret_cast<u32 *>(rg) + (size_t)dim * npad;
-            perm = scr + npad;
-            r_nlo = perm + npad;
+            u32 *rscr = reinterpret_cast<u32 *>(rg) + (size_t)dim * npad;
+            r_nlo = rscr + 2 * (size_t)npad;
             r_box = reinterpret_cast<float *>(r_nlo + ((S + 1 + 31) & ~31u));
+            if (a.in_smem & 1) {   // small cloud: build in shared memory, export the permuted cloud at the end
+                r_q = reinterpret_cast<float *>(rg);
+                r_perm = rscr + npad;
+            } else {               // big cloud: build in place in the region (L2)
+                q = reinterpret_cast<float *>(rg);
+                scr = rscr;
+                perm = rscr + npad;
+            }
         }
 
         // ---- stage: row-major -> SoA, identity permutation ---------------------------------------------
@@ -258,6 +266,11 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
         if (r_nlo) {
             for (u32 s = tid; s <= S; s += T) r_nlo[s] = nlo[s];
             for (u32 e = tid; e < S * 2 * dim; e += T) r_box[e] = fbox[e];
+        }
+        if (r_q) {
+            for (u32 c = 0; c < dim; ++c)
+                for (u32 i = tid; i < n; i += T) r_q[(size_t)c * npad + i] = q[(size_t)c * npad + i];
+            for (u32 i = tid; i < n; i += T) r_perm[i] = perm[i];
         }
         if (!a.out || a.region) continue;
 
