@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-fmad=false",           # bit-exact parity: no FMA contraction anywhere (the kernels also use *_rn)
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
-CU = ["vanilla.cu", "kdline.cu", "kdline_async.cu", "kdline_warp.cu", "kdbuild.cu", "capi.cu"]
+CU = ["vanilla.cu", "kdline.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_dist.cu", "kdbuild.cu", "capi.cu"]
 HDR = ["common.cuh", "kdcommon.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
 
 

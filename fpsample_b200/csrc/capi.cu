@@ -218,7 +218,8 @@ struct KdLayout {
     KdlinePlan pl;
     AsyncPlan ap;
     WarpPlan wp;
-    bool async, gridbuild, warp;
+    DistPlan dp;
+    bool async, gridbuild, warp, dist;
     size_t region_off, region_stride, aux_off, counter_off, total;
 };
 
@@ -240,8 +241,11 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         L->total = L->counter_off + 256;
         return cudaSuccess;
     }
-    L->async = !build_only && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
-    if (L->async) {
+    // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
+    // (kdline_async.cu) covers what is left (2^h > 512 buckets)
+    L->dist = !build_only && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
+    L->async = !build_only && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
+    if (L->async || L->dist) {
         // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
         L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
         if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
@@ -287,6 +291,22 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
                               reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
                               (u32)dim, (u32)k, (u32)h, st));
+        return FPS_OK;
+    }
+    if (L.dist) {
+        a.region = static_cast<unsigned char *>(ws) + L.region_off;
+        a.region_stride = L.region_stride;
+        set_plan("%s + kdline_dist_kernel<DIM=%d> clouds=%zu clusters=%u cluster=%u threads=%u buckets/CTA=%u "
+                 "candidates/CTA=%u smem=%zu region/cloud=%zu",
+                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)",
+                 L.dp.dimp, B, L.dp.clusters, L.dp.C, L.dp.threads, L.dp.NB, L.dp.M, L.dp.smem, L.region_stride);
+        if (L.gridbuild)
+            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
+                                   (u32)n, (u32)dim, (u32)h, st));
+        else
+            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        CK(launch_kdline_dist(L.dp, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h,
+                              st));
         return FPS_OK;
     }
     if (L.async) {
@@ -451,6 +471,8 @@ int fps_b200_debug_counters(uint64_t *out16) {
     CK(cudaDeviceSynchronize());
     if (getenv("FPS_B200_DBG_WARP"))
         CK(warp_debug_counters(reinterpret_cast<u64 *>(out16)));
+    else if (getenv("FPS_B200_DBG_DIST"))
+        CK(dist_debug_counters(reinterpret_cast<u64 *>(out16)));
     else
         CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
     return FPS_OK;

@@ -88,6 +88,7 @@ cudaError_t launch_kdline_async(const AsyncPlan &pl, unsigned char *region, size
 
 cudaError_t async_debug_counters(u64 *out16);
 cudaError_t warp_debug_counters(u64 *out16);
+cudaError_t dist_debug_counters(u64 *out16);
 
 // ---- kd-line, one warp per cloud over prebuilt regions, records in shared memory or tensor memory (kdline_warp.cu) --
 struct WarpPlan {
@@ -98,6 +99,16 @@ struct WarpPlan {
 bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpPlan *pl);
 cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
+
+// ---- kd-line, buckets distributed over the CTAs of a cluster, several picks per DSMEM all-gather (kdline_dist.cu) -----
+struct DistPlan {
+    int dimp;
+    u32 C, NB, M, threads, clusters;
+    size_t smem;
+};
+bool plan_kdline_dist(size_t n, size_t dim, size_t h, size_t B, int n_sms, DistPlan *pl);
+cudaError_t launch_kdline_dist(const DistPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
+                               u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
 
 // ---- kd-line build with the whole grid per level (kdbuild.cu), into the same per-cloud regions -------------
 size_t kd_gridbuild_aux_bytes(size_t n, size_t dim, size_t h);

@@ -27,6 +27,12 @@ for _ in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print(f"{wl} {algo} B={B}: min {min(ts):.3f} ms mean {sum(ts)/len(ts):.3f} ms -> {B/min(ts)*1e3:.1f} clouds/s | {capi.last_plan()}")
+if algo == "kdline" and "dist" in capi.last_plan():
+    os.environ["FPS_B200_DBG_DIST"] = "1"
+    o = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(o.ctypes.data)
+    it = max(int(o[0]), 1)
+    if int(o[0]): print("  dist dbg (cluster 0, CTA 0): iterations %d picks/iter %.2f | per iteration: cand+send %.0f wait %.0f select %.0f tests %.0f flush %.0f = %.0f cyc | flushed buckets/iter (this CTA) %.2f items/iter %.2f" % (
+        o[0], o[1] / it, o[2] / it, o[3] / it, o[4] / it, o[5] / it, o[6] / it, sum(int(x) for x in o[2:7]) / it, o[7] / it, o[8] / it))
 if algo == "kdline" and "async" in capi.last_plan():
     d = capi.debug_counters(); it = max(d["iterations"], 1)
     print("  dbg:", d, "| per iteration:", {k: round(v / it, 1) for k, v in d.items() if k.startswith("cyc")}, "picks/iter %.2f" % (d["picks"] / it))
