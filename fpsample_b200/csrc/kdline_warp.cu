@@ -58,11 +58,12 @@ __device__ __forceinline__ void sts128(u32 a, float x, float y, float z, float w
 // ---- the two point stores ---------------------------------------------------------------------------------------
 // component c (0..DIM-1 coordinates, DIM = running distance) of position (chunk, lane)
 struct SmemStore {
+    static constexpr bool kTrackCoords = false;
     u32 base;   // shared-space byte address of this warp's slot
     u32 lst;    // words per (component, lane) row: nch + 4 (16-byte aligned rows, conflict-free 128-bit access)
     __device__ __forceinline__ u32 addr(u32 comp, u32 lane, u32 chunk) const { return base + ((comp * 32u + lane) * lst + chunk) * 4u; }
     // 8 consecutive chunks starting at a multiple of 4
-    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U]) const {
+    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
         const u32 a = addr(comp, lane, cb);
         const float4 f0 = lds128(a), f1 = lds128(a + 16u);
         v[0] = f0.x, v[1] = f0.y, v[2] = f0.z, v[3] = f0.w, v[4] = f1.x, v[5] = f1.y, v[6] = f1.z, v[7] = f1.w;
@@ -83,9 +84,10 @@ struct SmemStore {
 };
 
 struct TmemStore {
+    static constexpr bool kTrackCoords = false;
     u32 base;   // tensor-memory address of this warp's lane quarter: (32 * (warp % 4)) << 16 | first column
     u32 nch;    // columns per component
-    __device__ __forceinline__ void load8(u32 comp, u32, u32 cb, float (&v)[W_U]) const {
+    __device__ __forceinline__ void load8(u32 comp, u32, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
         u32 w[W_U];
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                      : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
@@ -112,6 +114,42 @@ struct TmemStore {
         wait_ld();
 #pragma unroll
         for (int c = 0; c < DIM; ++c) r[c] = __uint_as_float(__shfl_sync(FULL, w[c], p & 31u));
+    }
+};
+
+// Points stay in the per-cloud region in global memory (L2 / HBM): for big clouds in big batches, where throughput
+// comes from hundreds of clouds in flight (one warp each) and the governing roofline is HBM bandwidth -- 4(D+2)
+// bytes per point-update.  A warp access is 32 consecutive positions = one 128-byte line per component.
+struct GlobalStore {
+    static constexpr bool kTrackCoords = true;   // a point lookup would be an L2 / HBM round trip on the pick path
+    const float *q;   // [dim][npad]
+    float *dis;       // [npad]
+    u32 npad, n;
+    // comp < ncomp: a coordinate; ncomp <= comp < DIM (padding dims of the template): 0; comp == DIM: the distance
+    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 ncomp, bool is_dis) const {
+#pragma unroll
+        for (int u = 0; u < W_U; ++u) {
+            const u32 p = (cb + u) * 32 + lane;
+            v[u] = 0.0f;
+            if (p < n) {
+                if (is_dis) v[u] = __ldcg(dis + p);
+                else if (comp < ncomp) v[u] = __ldg(q + (size_t)comp * npad + p);
+            }
+        }
+    }
+    __device__ __forceinline__ void wait_ld() const {}
+    __device__ __forceinline__ void store8(u32, u32 lane, u32 cb, const float (&v)[W_U]) const {   // distances only
+#pragma unroll
+        for (int u = 0; u < W_U; ++u) {
+            const u32 p = (cb + u) * 32 + lane;
+            if (p < n) __stcg(dis + p, v[u]);
+        }
+    }
+    __device__ __forceinline__ void wait_st() const {}
+    template <int DIM>
+    __device__ __forceinline__ void load_point(u32 p, u32, float (&r)[DIM]) const {
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) r[c] = __ldg(q + (size_t)c * npad + p);
     }
 };
 
@@ -145,7 +183,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
     // ---- stage the permuted cloud into this warp's store; distances start at FLT_MAX (Point.h:61-65) ---------
     for (u32 cb = 0; cb < nch; cb += W_U) {
 #pragma unroll
-        for (int c = 0; c <= DIM; ++c) {
+        for (int c = ST::kTrackCoords ? DIM : 0; c <= DIM; ++c) {   // a global store holds the coordinates already
             float v[W_U];
 #pragma unroll
             for (int u = 0; u < W_U; ++u) {
@@ -239,12 +277,15 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             const u32 c1b = (hi - 1) >> 5;
             float best = -1.0f;
             u32 bi = W_NONE;
+            float bc[DIM];   // coordinates of this lane's best point (global store only)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) bc[c] = 0.0f;
             for (u32 cb0 = (lo >> 5) & ~3u; cb0 <= c1b; cb0 += W_U) {
                 const u32 cb = min(cb0, nch - W_U);
                 float x[DIM][W_U], v[W_U], old[W_U];
 #pragma unroll
-                for (int c = 0; c < DIM; ++c) st.load8(c, lane, cb, x[c]);
-                st.load8(DIM, lane, cb, old);
+                for (int c = 0; c < DIM; ++c) st.load8(c, lane, cb, x[c], dim, false);
+                st.load8(DIM, lane, cb, old, dim, true);
                 st.wait_ld();
 #pragma unroll
                 for (int u = 0; u < W_U; ++u) v[u] = old[u];
@@ -280,6 +321,10 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                     if (in && v[u] > best) {   // ascending p: a lane keeps its first maximum
                         best = v[u];
                         bi = p;
+                        if constexpr (ST::kTrackCoords) {
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) bc[c] = x[c][u];
+                        }
                     }
                 }
                 st.store8(DIM, lane, cb, v);
@@ -290,7 +335,12 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             const u32 m = __reduce_max_sync(FULL, __float_as_uint(pv));
             const u32 qpos = __reduce_min_sync(FULL, (__float_as_uint(pv) == m) ? bi : W_NONE);
             float mc[DIM];
-            st.load_point(qpos, lane, mc);
+            if constexpr (ST::kTrackCoords) {
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) mc[c] = __shfl_sync(FULL, bc[c], qpos & 31u);
+            } else {
+                st.load_point(qpos, lane, mc);
+            }
             if (lane == (b & 31u)) {
 #pragma unroll
                 for (int j = 0; j < BPL; ++j)
@@ -319,8 +369,24 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             }
         }
         const u32 M = __reduce_max_sync(FULL, kmax);
-        cur = __reduce_min_sync(FULL, (cand != W_NONE && kmax == M) ? cand : W_NONE);
-        st.load_point(cur, lane, r);
+        const u32 mine = (cand != W_NONE && kmax == M) ? cand : W_NONE;
+        cur = __reduce_min_sync(FULL, mine);
+        if constexpr (ST::kTrackCoords) {   // the owner lane holds the max point's coordinates
+            float cm[DIM];
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) cm[c] = 0.0f;
+#pragma unroll
+            for (int j = 0; j < BPL; ++j)
+                if (((valid >> j) & 1u) && bpos[j] == cur) {
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) cm[c] = bmc[j][c];
+                }
+            const u32 src = __ffs(__ballot_sync(FULL, mine == cur)) - 1;   // positions are unique: exactly one lane
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) r[c] = __shfl_sync(FULL, cm[c], src);
+        } else {
+            st.load_point(cur, lane, r);
+        }
         // ---- output: positions are turned into original ids 32 picks at a time (wrapper.hpp:57-59) -----------------
         if ((t & 31u) == 0) {
             out[t - 32 + lane] = (u64)__ldg(perm + mypos);
@@ -394,6 +460,30 @@ __global__ void __launch_bounds__(512, 1) kdline_warp_kernel(WarpArgs a) {
     }
 }
 
+// the same per-cloud code over points left in global memory: every warp of the CTA takes clouds
+template <int DIM, int BPL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) kdline_warpg_kernel(WarpArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const u32 warp = warp_id(), lane = lane_id();
+    const u32 nw = blockDim.x >> 5;
+    unsigned char *meta = smem_raw + (size_t)warp * a.meta_bytes;
+    const u32 pend = smem_u32(meta);
+    u32 *nlo_s = reinterpret_cast<u32 *>(meta + (size_t)a.R * a.S * ((DIM + 3) / 4) * 16);
+    u32 cloud = warp * gridDim.x + blockIdx.x;
+    while (cloud < a.B) {
+        unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
+        GlobalStore st;
+        st.q = reinterpret_cast<const float *>(rg);
+        st.dis = reinterpret_cast<float *>(rg) + (size_t)a.dim * a.npad;
+        st.npad = a.npad;
+        st.n = a.n;
+        warp_cloud<DIM, BPL>(a, st, cloud, nlo_s, pend);
+        u32 nxt = 0;
+        if (lane == 0) nxt = atomicAdd(a.counter, 1u);
+        cloud = __shfl_sync(FULL, nxt, 0) + nw * gridDim.x;
+    }
+}
+
 // ======================================================================================================
 //  host side
 // ======================================================================================================
@@ -405,7 +495,6 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         if (atoi(e) == 0) return false;
     const size_t S = (size_t)1 << h;
     const int dimp = warp_dim((int)dim);
-    if (S > 32 && dimp > 4) return false;   // 4 buckets per lane only with small records (register budget)
     const size_t nch = (((n + 31) / 32) + W_U - 1) / W_U * W_U;
     const size_t slot = (size_t)(dimp + 1) * 32 * (nch + 4) * 4;
     u32 tm = ((size_t)(dimp + 1) * nch <= W_TMEM_COLS) ? 4u : 0u;
@@ -420,7 +509,34 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
     const size_t Rmin = lazy ? 3 : 1;
     u32 sw = 0;
     while (sw < W_MAX_SMEM_WARPS && (sw + 1 + tm) * meta_of(Rmin) + (sw + 1) * slot <= cap) ++sw;
-    if (sw + tm == 0) return false;
+    if (S > 32 && dimp > 4) sw = tm = 0;   // on chip, 4 buckets per lane only with small records (register budget)
+    if (sw + tm == 0) {
+        // not on chip: points stay in global memory, one warp per cloud, worth it only when the batch keeps every SM
+        // busy with many clouds (throughput from clouds in flight, HBM-bound); small batches go to the cluster kernels
+        size_t minB = (size_t)4 * n_sms;
+        if (const char *e = getenv("FPS_B200_WARP_GLOBAL_MINB")) minB = (size_t)atol(e);
+        if (B < minB) return false;
+        const u32 threads = dimp <= 4 ? 512 : 256;
+        const size_t nwg = threads / 32;
+        size_t R = Rmin;
+        const size_t budget = threads == 256 ? 100 * 1024 : cap;   // 256-thread CTAs run two per SM
+        while (lazy && R < W_MAXR && nwg * meta_of(R + 1) <= budget) ++R;
+        if (nwg * meta_of(R) > cap) return false;
+        pl->dimp = dimp;
+        pl->rs = (u32)R;
+        pl->bpl = S <= 32 ? 1 : 4;
+        pl->n_tmem_warps = 0;
+        pl->n_smem_warps = (u32)nwg;
+        pl->slot_bytes = 0;
+        pl->meta_bytes = (u32)meta_of(R);
+        pl->lazy = lazy ? 1 : 0;
+        pl->nch = (u32)nch;
+        pl->global = 1;
+        pl->smem = nwg * meta_of(R);
+        const size_t gmax = (size_t)n_sms * (threads == 256 ? 2 : 1);   // spread over every SM before stacking warps
+        pl->grid = (u32)(B < gmax ? B : gmax);
+        return true;
+    }
     const size_t nw = sw + tm;
     size_t R = Rmin;
     while (lazy && R < W_MAXR && nw * meta_of(R + 1) + sw * slot <= cap) ++R;
@@ -437,6 +553,7 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
     pl->grid = (u32)grid;
     pl->lazy = lazy ? 1 : 0;
     pl->nch = (u32)nch;
+    pl->global = 0;
     pl->smem = nw * meta_of(R) + sw * slot;
     // tensor memory is allocated whole: never let a second CTA of this kernel become resident on the SM
     if (tm && pl->smem < 120 * 1024) pl->smem = 120 * 1024;
@@ -449,6 +566,15 @@ static cudaError_t launch_warp_t(const WarpPlan &pl, const WarpArgs &a, cudaStre
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     kern<<<pl.grid, 32 * (pl.n_tmem_warps + pl.n_smem_warps), pl.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int DIM, int BPL, int MAXT>
+static cudaError_t launch_warpg_t(const WarpPlan &pl, const WarpArgs &a, cudaStream_t st) {
+    auto kern = kdline_warpg_kernel<DIM, BPL, MAXT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<pl.grid, MAXT, pl.smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -479,6 +605,17 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;
+    if (pl.global) {
+        switch (pl.dimp) {
+            case 2: e = b1 ? launch_warpg_t<2, 1, 512>(pl, a, st) : launch_warpg_t<2, 4, 512>(pl, a, st); break;
+            case 3: e = b1 ? launch_warpg_t<3, 1, 512>(pl, a, st) : launch_warpg_t<3, 4, 512>(pl, a, st); break;
+            case 4: e = b1 ? launch_warpg_t<4, 1, 512>(pl, a, st) : launch_warpg_t<4, 4, 512>(pl, a, st); break;
+            case 6: e = b1 ? launch_warpg_t<6, 1, 256>(pl, a, st) : launch_warpg_t<6, 4, 256>(pl, a, st); break;
+            default: e = b1 ? launch_warpg_t<7, 1, 256>(pl, a, st) : launch_warpg_t<7, 4, 256>(pl, a, st); break;
+        }
+        count_launch();
+        return e;
+    }
     switch (pl.dimp) {
         case 2: e = b1 ? launch_warp_t<2, 1>(pl, a, st) : launch_warp_t<2, 4>(pl, a, st); break;
         case 3: e = b1 ? launch_warp_t<3, 1>(pl, a, st) : launch_warp_t<3, 4>(pl, a, st); break;

@@ -114,7 +114,7 @@ def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle):
     near-empty buckets must not disturb its upper-bound logic."""
     g = synth.grid_ties(n + h, n, d, levels=levels)
     got = capi.kdline(g, k, h, s)
-    assert "kdline_dist_kernel" in capi.last_plan() or "kdline_async_kernel" in capi.last_plan(), capi.last_plan()
+    assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warpg_kernel")), capi.last_plan()
     np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
 
 
@@ -123,9 +123,39 @@ def test_async_batches_and_cluster_sizes(oracle):
         pcs = synth.uniform_batch(8000 + B, B, n, 3)
         st = (np.arange(B) * 7) % n
         got = capi.kdline_batch(pcs, k, h, st, devices=[0])
-        assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warp_kernel")), capi.last_plan()
+        assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warp")), capi.last_plan()
         want = np.stack([oracle.kdline(pcs[b], k, h, int(st[b])) for b in range(B)])
         np.testing.assert_array_equal(got, want, err_msg=capi.last_plan())
+
+
+@pytest.mark.parametrize("env", [{"FPS_B200_WARP_GLOBAL_MINB": "1"}, {"FPS_B200_DIST": "1"}, {"FPS_B200_WARP_LAZY": "0"},
+                                 {"FPS_B200_WARP_TMEM": "0"}])
+def test_alternative_samplers(env, oracle):
+    """every kd-line sampler must give the reference's indices, not only the one the planner prefers: the
+    one-warp-per-cloud kernel over global memory (big batches), the distributed-bucket cluster kernel (opt-in),
+    the eager variant of the warp kernel and its shared-memory-only placement."""
+    os.environ.update(env)
+    try:
+        want_plan = {"FPS_B200_WARP_GLOBAL_MINB": "kdline_warpg_kernel", "FPS_B200_DIST": "kdline_dist_kernel",
+                     "FPS_B200_WARP_LAZY": "eager", "FPS_B200_WARP_TMEM": "tmem 0"}[next(iter(env))]
+        big = next(iter(env)) in ("FPS_B200_WARP_GLOBAL_MINB", "FPS_B200_DIST")
+        shapes = [(30000, 3, 900, 7, 5, "u"), (20000, 6, 500, 6, 0, "u"), (40000, 2, 800, 5, 3, "g"), (50000, 1, 700, 5, 1, "g"),
+                  (25000, 3, 600, 7, 2, "l")] if big else \
+                 [(4096, 3, 1024, 5, 0, "u"), (3000, 6, 500, 5, 7, "u"), (5000, 2, 700, 7, 1, "g"), (4096, 3, 600, 6, 9, "l")]
+        for n, d, k, h, s, gen in shapes:
+            pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=37),
+                  "l": lambda: synth.lidar(n, n)}[gen]()
+            got = capi.kdline(pc, k, h, s)
+            assert want_plan in capi.last_plan(), capi.last_plan()
+            np.testing.assert_array_equal(got, oracle.kdline(pc, k, h, s), err_msg=capi.last_plan())
+        if big:
+            pcs = synth.uniform_batch(6100, 12, 20000, 3)
+            got = capi.kdline_batch(pcs, 300, 7, np.arange(12) * 3, devices=[0])
+            assert want_plan in capi.last_plan(), capi.last_plan()
+            np.testing.assert_array_equal(got, np.stack([oracle.kdline(pcs[b], 300, 7, 3 * b) for b in range(12)]))
+    finally:
+        for k_ in env:
+            os.environ.pop(k_, None)
 
 
 def test_unaligned_and_strided_inputs(oracle):
