@@ -258,8 +258,9 @@ def gpu_arm(args):
     clocks = Clocks(local)
     clocks.start()
     l0 = capi.kernel_launches()
-    evs = []
+    evs, phases = [], []
     barrier()
+    capi.phase_timing(True)      # CUDA events on OUR stream around the build and the sampling launch of every step
     with torch.cuda.stream(stream):
         for _ in range(args.steps):
             flush.fill_(1)                                  # L2 flush, outside the event pair
@@ -268,6 +269,8 @@ def gpu_arm(args):
             launch()
             e1.record(stream)
             evs.append((e0, e1))
+            phases.append(capi.last_phase_ms())             # waits for this step; the next step starts cold again
+    capi.phase_timing(False)
     barrier()
     launches = capi.kernel_launches() - l0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
@@ -315,11 +318,20 @@ def gpu_arm(args):
         fp32_peak = SM_COUNT * LANES * sm_mhz * 1e6 / 1e12        # T lane-op/s, no FMA allowed on this path
         pu, bt = algorithmic_work(algo, args.workload)
         ops_cloud = pu * (3 * d + 1) + bt * (8 * d)
-        t_launch = (statistics.mean(step_ms) * 1e-3)               # one launch per step on this rank
+        build_ms = statistics.mean(p[0] for p in phases)
+        sample_ms = statistics.mean(p[1] for p in phases)
+        t_launch = sample_ms * 1e-3                                # the dominant kernel's own duration (CUDA events)
+        names = [x.split("(")[0].split("<")[0].strip() for x in plan.split(" + ")]
+        kernel = next((x for x in names if "kdline_" in x and x != "kdline_kernel"), names[0]).split(" ")[0]
         fp32_ach = ops_cloud * B / t_launch / 1e12
-        bytes_cloud = n * d * 4 + k * 8
+        streamed = "kdline_warpg" in plan or "vanilla_grid" in plan   # points re-read from L2/HBM on every update
+        bytes_cloud = pu * 4 * (d + 2) if streamed else n * d * 4 + k * 8
         hbm_ach = bytes_cloud * B / t_launch / 1e9
         bf_ops = float(n) * (k - 1) * (3 * d + 1) * B
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tj):
+            traffic = json.load(open(tj)).get(f"{args.workload}:{algo}", {}).get("dram_bytes_per_launch")
         line = {
             "metric": "clouds/sec (BxN->K)", "value": value, "unit": "clouds/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -335,18 +347,25 @@ def gpu_arm(args):
                     "matches_device_path": same},
             "gpu_launches": int(launches),
             "clocks": clk,
+            "phases_ms": {"kd_build": build_ms, "sampling": sample_ms, "step": statistics.mean(step_ms),
+                          "how": "CUDA events recorded by the library on the launching stream around its own launches (fps_b200_phase_timing)"},
             "roofline": {"bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "Tlaneop/s",
-                         "frac": fp32_ach / fp32_peak, "traffic": None,
-                         "kernel": plan.split(" ")[0],
+                         "frac": fp32_ach / fp32_peak, "traffic": traffic,
+                         "kernel": kernel, "kernel_ms": sample_ms, "governs": not streamed,
                          "note": f"governing roofline per SURVEY.md 8(d): FP32 pipe without FMA = 148 SM x 128 lanes x {sm_mhz:.0f} MHz ({how}); "
                                  f"algorithmic work = reference algorithm's {pu:.0f} point-updates x {3 * d + 1} + {bt:.0f} bucket tests x {8 * d} lane-ops per cloud",
                          "brute_force_equiv_frac": bf_ops / t_launch / 1e12 / fp32_peak},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_gbs, "unit": "GB/s",
-                             "frac": hbm_ach / hbm_gbs, "traffic": None,
-                             "note": f"compulsory bytes only: {bytes_cloud} B per cloud (coords in, uint64 indices out); clouds stay on chip for all k rounds; peak {how}"},
+                             "frac": hbm_ach / hbm_gbs, "traffic": traffic, "kernel": kernel, "governs": streamed,
+                             "note": (f"streamed path: {pu:.0f} point-updates x {4 * (d + 2)} B per cloud re-read from L2/HBM (SURVEY.md 8(d)); peak {how}"
+                                      if streamed else
+                                      f"compulsory bytes only: {bytes_cloud:.0f} B per cloud (coords in, uint64 indices out); clouds stay on chip for all k rounds; peak {how}")},
             "cpu_baseline": cpu,
             "parity_checked_clouds": checked,
         }
+        if streamed:   # the governing roofline goes under "roofline"
+            line["roofline"], line["roofline_hbm"] = line["roofline_hbm"], line["roofline"]
+            line["roofline_fp32"] = line.pop("roofline_hbm")
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

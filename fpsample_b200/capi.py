@@ -29,6 +29,8 @@ EXPORTS = {
     "fps_b200_last_plan": (ctypes.c_char_p, []),
     "fps_b200_kernel_launches": (ctypes.c_uint64, []),
     "fps_b200_debug_counters": (ctypes.c_int, [ctypes.c_void_p]),
+    "fps_b200_phase_timing": (None, [ctypes.c_int]),
+    "fps_b200_last_phase_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fps_b200_host_free": (None, [ctypes.c_void_p]),
 }
@@ -77,6 +79,17 @@ def debug_counters():
     names = ("iterations", "picks", "stalled_iterations", "cyc_poll_warptop", "cyc_wait_warps", "cyc_blocktop",
              "cyc_tests")
     return {k: int(v) for k, v in zip(names, out)}
+
+
+def phase_timing(enable: bool) -> None:
+    lib().fps_b200_phase_timing(1 if enable else 0)
+
+
+def last_phase_ms():
+    """(build_ms, sample_ms) of this thread's last *_dev call made with phase timing enabled."""
+    b, s = ctypes.c_float(0), ctypes.c_float(0)
+    _check("fps_b200_last_phase_ms", lib().fps_b200_last_phase_ms(ctypes.byref(b), ctypes.byref(s)))
+    return float(b.value), float(s.value)
 
 
 def device_count() -> int:

@@ -43,6 +43,22 @@ static void set_plan(const char *fmt, ...) {
         }                                                                                     \
     } while (0)
 
+// ---- optional phase timing of the *_dev entries (bench.py: the dominant kernel's own duration) -----------------------
+// When enabled, the calling thread's next *_dev call records CUDA events on ITS stream around the build and the
+// sampling launches; fps_b200_last_phase_ms synchronises on them.  Off by default: no events, no overhead.
+static std::atomic<int> g_phase_timing{0};
+struct PhaseTimer {
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    bool armed = false;
+    void mark(int i, cudaStream_t st) {
+        if (!g_phase_timing.load(std::memory_order_relaxed)) return;
+        if (!ev[i]) cudaEventCreate(&ev[i]);
+        cudaEventRecord(ev[i], st);
+        if (i == 2) armed = true;
+    }
+};
+static thread_local PhaseTimer tl_phase;
+
 // ---- devices ---------------------------------------------------------------------------------------------
 struct Buf {
     void *p = nullptr;
@@ -186,7 +202,10 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
         a.slice = L.vp.slice;
         set_plan("vanilla_cluster_kernel<DIM=%d,PPT=%d> clouds=%zu cluster=%u slice=%u smem=%zu", L.vp.dimp, L.vp.ppt, B,
                  L.vp.C, L.vp.slice, L.vp.smem);
+        tl_phase.mark(0, st);
+        tl_phase.mark(1, st);
         CK(launch_vanilla_cluster(L.vp, a, (u32)B, st));
+        tl_phase.mark(2, st);
         count_launch();
         return FPS_OK;
     }
@@ -209,7 +228,10 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
     g.n_starts = (u32)(d_starts ? n_starts : 0);
     set_plan("vanilla_grid_kernel clouds=%zu groups=%u G=%u slice=%u smem=%zu", B, L.gp.groups, L.gp.G, L.gp.slice,
              L.gp.smem);
+    tl_phase.mark(0, st);
+    tl_phase.mark(1, st);
     CK(launch_vanilla_grid(L.gp, g, st));
+    tl_phase.mark(2, st);
     count_launch();
     return FPS_OK;
 }
@@ -287,15 +309,19 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
                  "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
                  L.wp.global ? "g" : "", L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
                  L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
+        tl_phase.mark(0, st);
         CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        tl_phase.mark(1, st);
         CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
                               reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
                               (u32)dim, (u32)k, (u32)h, st));
+        tl_phase.mark(2, st);
         return FPS_OK;
     }
     if (L.dist) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
+        tl_phase.mark(0, st);
         set_plan("%s + kdline_dist_kernel<DIM=%d> clouds=%zu clusters=%u cluster=%u threads=%u buckets/CTA=%u "
                  "candidates/CTA=%u smem=%zu region/cloud=%zu",
                  L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)",
@@ -305,13 +331,16 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
                                    (u32)n, (u32)dim, (u32)h, st));
         else
             CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        tl_phase.mark(1, st);
         CK(launch_kdline_dist(L.dp, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h,
                               st));
+        tl_phase.mark(2, st);
         return FPS_OK;
     }
     if (L.async) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
+        tl_phase.mark(0, st);
         set_plan("%s + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
                  "cluster=%u threads=%u smem=%zu R=%u region/cloud=%zu",
                  L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
@@ -321,14 +350,19 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
                                    (u32)n, (u32)dim, (u32)h, st));
         else
             CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        tl_phase.mark(1, st);
         CK(launch_kdline_async(L.ap, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k,
                                (u32)h, st));
+        tl_phase.mark(2, st);
         return FPS_OK;
     }
     set_plan("kdline_kernel<DIM=%d> clouds=%zu grid=%u threads=%u smem=%zu placement=%s ws/cta=%zu", pl.dimp, B, pl.grid,
              pl.threads, pl.smem, pl.in_smem == 3 ? "smem" : (pl.in_smem == 2 ? "meta-smem,data-L2" : "L2"),
              pl.ws_stride);
+    tl_phase.mark(0, st);
+    tl_phase.mark(1, st);
     CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+    tl_phase.mark(2, st);
     return FPS_OK;
 }
 
@@ -355,7 +389,15 @@ static int run_shard(int dev, const ShardJob &j) {
         cx->ready = true;
     }
     const size_t in_per = j.n * j.dim * sizeof(float), out_per = j.k * sizeof(u64);
-    const size_t nch = j.B >= 256 ? 4 : (j.B >= 64 ? 2 : 1);
+    // chunks overlap the upload of one with the kernels of the other (two lanes); each chunk must still be a batch the
+    // samplers like: >= 1024 clouds (the one-warp-per-cloud kernels want every SM stacked) and >= 32 MB of input
+    size_t nch = 1;
+    {
+        const size_t by_bytes = (j.B * in_per) / (32u << 20), by_clouds = j.B / 1024;
+        nch = by_bytes < by_clouds ? by_bytes : by_clouds;
+        if (nch < 1) nch = 1;
+        if (nch > 8) nch = 8;
+    }
     const size_t chunk = (j.B + nch - 1) / nch;
     static_assert(sizeof(size_t) == sizeof(u64), "size_t must be 64-bit");
     int rc = FPS_OK;
@@ -475,6 +517,22 @@ int fps_b200_debug_counters(uint64_t *out16) {
         CK(dist_debug_counters(reinterpret_cast<u64 *>(out16)));
     else
         CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
+    return FPS_OK;
+}
+
+void fps_b200_phase_timing(int enable) { g_phase_timing.store(enable ? 1 : 0); }
+
+int fps_b200_last_phase_ms(float *build_ms, float *sample_ms) {
+    if (!tl_phase.armed) {
+        set_err("no timed *_dev call on this thread (enable fps_b200_phase_timing first)");
+        return FPS_ERR_ARG;
+    }
+    CK(cudaEventSynchronize(tl_phase.ev[2]));
+    float b = 0.f, s = 0.f;
+    CK(cudaEventElapsedTime(&b, tl_phase.ev[0], tl_phase.ev[1]));
+    CK(cudaEventElapsedTime(&s, tl_phase.ev[1], tl_phase.ev[2]));
+    if (build_ms) *build_ms = b;
+    if (sample_ms) *sample_ms = s;
     return FPS_OK;
 }
 

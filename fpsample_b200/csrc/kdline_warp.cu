@@ -28,7 +28,7 @@ constexpr u32 W_NONE = 0xffffffffu;
 constexpr int W_U = 8;                 // chunks (of 32 positions) per straight-line block of a bucket pass
 constexpr u32 W_MAX_SMEM_WARPS = 12;
 constexpr u32 W_TMEM_COLS = 512;
-constexpr u32 W_MAXR = 8;              // pending samples per bucket at most
+constexpr u32 W_MAXR = 12;             // pending samples per bucket at most
 
 #ifndef WDBG
 #define WDBG 0   // 1: per-phase clock64 counters of cloud 0 (scripts/run_one.py prints them)
@@ -516,11 +516,14 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         size_t minB = (size_t)4 * n_sms;
         if (const char *e = getenv("FPS_B200_WARP_GLOBAL_MINB")) minB = (size_t)atol(e);
         if (B < minB) return false;
-        const u32 threads = dimp <= 4 ? 512 : 256;
-        const size_t nwg = threads / 32;
-        size_t R = Rmin;
-        const size_t budget = threads == 256 ? 100 * 1024 : cap;   // 256-thread CTAs run two per SM
-        while (lazy && R < W_MAXR && nwg * meta_of(R + 1) <= budget) ++R;
+        // long pending lists matter more than warps per SM here: every early flush re-reads a bucket from HBM, and in
+        // 6-D the reference itself defers ~14 samples per pick.  Warps per CTA = what the lists
+        // leave room for (at least 4: each warp keeps (D+1) x 8 lines in flight).
+        const u32 maxt = dimp <= 4 ? 512 : 256;
+        size_t R = lazy ? (dimp <= 4 ? 6 : W_MAXR) : 1;
+        size_t nwg = maxt / 32;
+        while (nwg > 4 && nwg * meta_of(R) > cap) --nwg;
+        while (R > Rmin && nwg * meta_of(R) > cap) --R;
         if (nwg * meta_of(R) > cap) return false;
         pl->dimp = dimp;
         pl->rs = (u32)R;
@@ -533,7 +536,7 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         pl->nch = (u32)nch;
         pl->global = 1;
         pl->smem = nwg * meta_of(R);
-        const size_t gmax = (size_t)n_sms * (threads == 256 ? 2 : 1);   // spread over every SM before stacking warps
+        const size_t gmax = (size_t)n_sms;   // spread over every SM before stacking warps
         pl->grid = (u32)(B < gmax ? B : gmax);
         return true;
     }
@@ -574,7 +577,7 @@ static cudaError_t launch_warpg_t(const WarpPlan &pl, const WarpArgs &a, cudaStr
     auto kern = kdline_warpg_kernel<DIM, BPL, MAXT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
-    kern<<<pl.grid, MAXT, pl.smem, st>>>(a);
+    kern<<<pl.grid, 32 * pl.n_smem_warps, pl.smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -100,6 +100,11 @@ FPS_API const char *fps_b200_last_error(void);      /* thread-local description 
 FPS_API uint64_t fps_b200_kernel_launches(void);    /* kernels launched by this library in this process       */
 FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kernel/shape the last call picked  */
 FPS_API int fps_b200_debug_counters(uint64_t *out16); /* phase counters of the last kd-line cluster launch (diagnostics) */
+/* Phase timing of the *_dev entries (measurement only, off by default): when enabled, the calling thread's next
+ * *_dev call records CUDA events on its stream around the kd build launches and the sampling launch;
+ * fps_b200_last_phase_ms waits for them and returns both durations (build = 0 for the vanilla entry). */
+FPS_API void fps_b200_phase_timing(int enable);
+FPS_API int fps_b200_last_phase_ms(float *build_ms, float *sample_ms);
 FPS_API void *fps_b200_host_alloc(size_t bytes);    /* page-locked host memory for the host-pointer entries   */
 FPS_API void fps_b200_host_free(void *p);
 
