@@ -14,6 +14,7 @@
 #include "engine.h"
 
 namespace fps {
+cudaError_t kb_debug_counters(unsigned long long *out16);
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -513,6 +514,8 @@ int fps_b200_debug_counters(uint64_t *out16) {
     CK(cudaDeviceSynchronize());
     if (getenv("FPS_B200_DBG_WARP"))
         CK(warp_debug_counters(reinterpret_cast<u64 *>(out16)));
+    else if (getenv("FPS_B200_DBG_BUILD"))
+        CK(kb_debug_counters(reinterpret_cast<unsigned long long *>(out16)));
     else if (getenv("FPS_B200_DBG_DIST"))
         CK(dist_debug_counters(reinterpret_cast<u64 *>(out16)));
     else

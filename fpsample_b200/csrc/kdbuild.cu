@@ -92,7 +92,12 @@ __global__ void __launch_bounds__(256) gb_rootbox(GBArgs a) {
 
 // ---- gb_split: one warp per node ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) gb_split(GBArgs a) {
-    __shared__ __align__(16) float chainbuf[4][256];
+    __shared__ __align__(16) float ring[4][SS_STAGES * SS_TILE];   // one TMA ring per warp
+    __shared__ u64 bars[4][SS_STAGES];
+    if (lane_id() < SS_STAGES) mbar_init(smem_u32(&bars[warp_id()][lane_id()]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    u32 phase = 0;
     const u32 nn = 1u << a.lvl, stride = a.S >> a.lvl, half = stride >> 1;
     const u32 gw = blockIdx.x * (blockDim.x >> 5) + warp_id();
     if (gw >= a.B * nn) return;
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(128) gb_split(GBArgs a) {
             sd = c;
         }
     }
-    const float sum = seq_sum_staged(v.q + (size_t)sd * a.npad + lo, count, chainbuf[warp_id()]);
+    const float sum = seq_sum_tma(v.q + (size_t)sd * a.npad + lo, count, ring[warp_id()], bars[warp_id()], phase);
     const float val = __fdiv_rn(sum, __uint2float_rn(count));
     if (lane == 0) {
         v.A0[j] = __float_as_uint(val);

@@ -25,6 +25,8 @@
 #include "kdcommon.cuh"
 
 namespace fps {
+__device__ unsigned long long g_kb_dbg[16];
+#define KBDBG 0   // 1: per-phase clock64 counters of cloud 0 (scripts/time_build.py prints them)
 
 struct KdFixedSmem {
     u64 wslot[2][32];
@@ -116,8 +118,16 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
         }
         __syncthreads();
 
+#if KBDBG
+        unsigned long long kd[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long kt0 = clock64();
+        kd[0] = 0;
+#endif
         // ---- build -----------------------------------------------------------------------------------
         for (u32 lvl = 0; lvl < h; ++lvl) {
+#if KBDBG
+            long long ka = clock64();
+#endif
             const u32 nn = 1u << lvl, stride = S >> lvl, half = stride >> 1;
             const u32 ts = nn < NW ? NW / nn : 1u;  // warps per node
             const u32 nteams = NW / ts;
@@ -139,7 +149,9 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                             sd = c;
                         }
                     }
-                    float sum = seq_sum_staged(q + (size_t)sd * npad + lo, hi - lo, chainbuf);
+                    const float *col = q + (size_t)sd * npad + lo;
+                    const float sum = ((a.in_smem & 1) && !(a.region && !(a.in_smem & 1))) ? seq_sum_smem(col, hi - lo)
+                                                                                        : seq_sum_staged(col, hi - lo, chainbuf);
                     float val = __fdiv_rn(sum, __uint2float_rn(hi - lo));
                     if (lane == 0) {
                         A0[j] = __float_as_uint(val);
@@ -149,6 +161,9 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                 }
             }
             __syncthreads();
+#if KBDBG
+            { long long kb = clock64(); kd[1] += kb - ka; ka = kb; }
+#endif
             // P2: count '< val' per (node, rank) sub-range
             if (team < nteams) {
                 for (u32 j = team; j < nn; j += nteams) {
@@ -166,6 +181,9 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                 }
             }
             __syncthreads();
+#if KBDBG
+            { long long kb = clock64(); kd[2] += kb - ka; ka = kb; }
+#endif
             // P3: rank the misplaced elements (KDTreeBase.h:123-149 in closed form)
             if (team < nteams) {
                 for (u32 j = team; j < nn; j += nteams) {
@@ -204,6 +222,9 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                 }
             }
             __syncthreads();
+#if KBDBG
+            { long long kb = clock64(); kd[3] += kb - ka; ka = kb; }
+#endif
             // P4: swaps, child boundaries, child box init
             if (team < nteams) {
                 for (u32 j = team; j < nn; j += nteams) {
@@ -238,6 +259,9 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                 }
             }
             __syncthreads();
+#if KBDBG
+            { long long kb = clock64(); kd[4] += kb - ka; ka = kb; }
+#endif
             // P5: tight child boxes (KDTreeBase.h:112-116, 181-207)
             if (team < nteams) {
                 for (u32 j = team; j < nn; j += nteams) {
@@ -253,8 +277,15 @@ __global__ void __launch_bounds__(1024, 1) kdline_kernel(KdlineArgs a, u32 *work
                 }
             }
             __syncthreads();
+#if KBDBG
+            { long long kb = clock64(); kd[5] += kb - ka; ka = kb; }
+#endif
         }
 
+#if KBDBG
+        kd[6] = clock64() - kt0;
+        if (cloud == 0 && tid == 0) { for (int i = 0; i < 8; ++i) g_kb_dbg[i] = kd[i]; }
+#endif
         // ---- leaves: decode boxes to floats; optional export ---------------------------------------------
         float *fbox = reinterpret_cast<float *>(box);
         for (u32 e = tid; e < S * 2 * dim; e += T) fbox[e] = ord2f(box[e]);
@@ -424,6 +455,8 @@ cudaError_t plan_kdline(size_t n, size_t dim, size_t h, size_t B, int n_sms, Kdl
     pl->ws_bytes = 256 + grid * ws;
     return cudaSuccess;
 }
+
+cudaError_t kb_debug_counters(unsigned long long *out16) { return cudaMemcpyFromSymbol(out16, g_kb_dbg, sizeof(unsigned long long) * 16); }
 
 cudaError_t launch_kdline(const KdlinePlan &pl, KdlineArgs a, unsigned char *ws_base, cudaStream_t st) {
     u32 *counter = reinterpret_cast<u32 *>(ws_base);

@@ -21,3 +21,6 @@ for _ in range(5):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print(f"build only B={B} n={n} d={d} h={h}: min {min(ts):.3f} ms | {capi.last_plan()}")
+os.environ["FPS_B200_DBG_BUILD"] = "1"
+o = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(o.ctypes.data)
+print("  build dbg (cloud 0) cycles: P1 split+chain %d | P2 count %d | P3 rank %d | P4 swap %d | P5 boxes %d | all levels %d" % tuple(int(x) for x in o[1:7]))
