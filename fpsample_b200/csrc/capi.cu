@@ -308,7 +308,7 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         a.region_stride = L.region_stride;
         set_plan("kdline_kernel(build, 1 CTA per cloud) + kdline_warp%s_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
                  "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
-                 L.wp.global ? "g" : "", L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
+                 L.wp.global ? "g" : (L.wp.hybrid ? "(hybrid smem+tmem)" : ""), L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
                  L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
         tl_phase.mark(0, st);
         CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));

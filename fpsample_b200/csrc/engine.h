@@ -93,7 +93,7 @@ cudaError_t dist_debug_counters(u64 *out16);
 // ---- kd-line, one warp per cloud over prebuilt regions, records in shared memory or tensor memory (kdline_warp.cu) --
 struct WarpPlan {
     int dimp;
-    u32 rs /* pending samples per bucket */, bpl, n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, grid, lazy, nch, global;
+    u32 rs /* pending samples per bucket */, bpl, n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, grid, lazy, nch, global, hybrid;
     size_t smem;
 };
 bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpPlan *pl);

@@ -43,7 +43,7 @@ struct WarpArgs {
     u32 *counter;
     u32 B, n, npad, dim, k, S, nlo_pad;
     u32 nch;            // chunks per cloud, padded to a multiple of W_U
-    u32 n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, R, lazy;
+    u32 n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, R, lazy, hybrid;
 };
 
 __device__ __forceinline__ float4 lds128(u32 a) {
@@ -114,6 +114,30 @@ struct TmemStore {
         wait_ld();
 #pragma unroll
         for (int c = 0; c < DIM; ++c) r[c] = __uint_as_float(__shfl_sync(FULL, w[c], p & 31u));
+    }
+};
+
+// Coordinates in shared memory, running distances in tensor memory: a cloud of up to 16 384 points x 3 dims
+// (BASELINE.json cfg 3) is 192 KB of coordinates + 64 KB of distances -- more than either store alone, exactly what one
+// SM has when both are used.  One such warp per SM (its distances fill one lane quarter of TMEM).
+struct HybridStore {
+    static constexpr bool kTrackCoords = false;
+    SmemStore s;   // DIM components
+    TmemStore t;   // one component: the distance of chunk c is column c
+    u32 dimc;      // index of the distance component (= DIM of the kernel)
+    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
+        if (comp == dimc) t.load8(0, lane, cb, v);
+        else s.load8(comp, lane, cb, v);
+    }
+    __device__ __forceinline__ void wait_ld() const { t.wait_ld(); }
+    __device__ __forceinline__ void store8(u32 comp, u32 lane, u32 cb, const float (&v)[W_U]) const {
+        if (comp == dimc) t.store8(0, lane, cb, v);
+        else s.store8(comp, lane, cb, v);
+    }
+    __device__ __forceinline__ void wait_st() const { t.wait_st(); }
+    template <int DIM>
+    __device__ __forceinline__ void load_point(u32 p, u32 lane, float (&r)[DIM]) const {
+        s.load_point(p, lane, r);
     }
 };
 
@@ -417,7 +441,7 @@ __global__ void __launch_bounds__(512, 1) kdline_warp_kernel(WarpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 tbase_s;
     const u32 warp = warp_id(), lane = lane_id();
-    const u32 nw = a.n_tmem_warps + a.n_smem_warps;
+    const u32 nw = a.hybrid ? a.n_tmem_warps : a.n_tmem_warps + a.n_smem_warps;
 
     if (a.n_tmem_warps) {   // whole tensor memory of this SM: one CTA per SM by construction (see plan)
         if (warp == 0) {
@@ -438,7 +462,15 @@ __global__ void __launch_bounds__(512, 1) kdline_warp_kernel(WarpArgs a) {
     // afterwards clouds are handed out dynamically
     u32 cloud = warp * gridDim.x + blockIdx.x;
     while (cloud < a.B) {
-        if (warp < a.n_tmem_warps) {
+        if (a.hybrid) {   // warp w: coordinates in shared-memory slot w, distances in TMEM lane quarter w
+            HybridStore st;
+            st.s.base = smem_u32(slots + (size_t)warp * a.slot_bytes);
+            st.s.lst = a.nch + 4;
+            st.t.base = tbase_s + ((warp * 32u) << 16);
+            st.t.nch = a.nch;
+            st.dimc = DIM;
+            warp_cloud<DIM, BPL>(a, st, cloud, nlo_s, pend);
+        } else if (warp < a.n_tmem_warps) {
             TmemStore st;
             st.base = tbase_s + ((warp * 32u) << 16);
             st.nch = a.nch;
@@ -510,6 +542,37 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
     u32 sw = 0;
     while (sw < W_MAX_SMEM_WARPS && (sw + 1 + tm) * meta_of(Rmin) + (sw + 1) * slot <= cap) ++sw;
     if (S > 32 && dimp > 4) sw = tm = 0;   // on chip, 4 buckets per lane only with small records (register budget)
+    pl->hybrid = 0;
+    if (sw + tm == 0 && !(S > 32 && dimp > 4) && nch <= W_TMEM_COLS) {
+        // neither store alone holds the cloud: coordinates in shared memory + distances in TMEM (one lane quarter each)
+        const size_t cslot = (size_t)dimp * 32 * (nch + 4) * 4;
+        u32 hw = 0;
+        while (hw < 4 && (hw + 1) * (meta_of(Rmin) + cslot) <= cap) ++hw;
+        // measured on cfg 3 (64 x 16384 x 3 -> 4096, h=7): 6.7 ms against 5.8 ms for the async cluster kernel (4 buckets
+        // per lane + TMEM round trips make the lone warp's pick ~2900 cycles), so it is opt-in: FPS_B200_WARP_HYBRID=1
+        bool hyb = false;
+        if (const char *e = getenv("FPS_B200_WARP_HYBRID")) hyb = hw > 0 && atoi(e) != 0;
+        if (hyb) {
+            size_t R = Rmin;
+            while (lazy && R < W_MAXR && hw * (meta_of(R + 1) + cslot) <= cap) ++R;
+            size_t grid = B < (size_t)n_sms ? B : (size_t)n_sms;
+            pl->dimp = dimp;
+            pl->rs = (u32)R;
+            pl->bpl = S <= 32 ? 1 : 4;
+            pl->n_tmem_warps = hw;
+            pl->n_smem_warps = 0;
+            pl->slot_bytes = (u32)cslot;
+            pl->meta_bytes = (u32)meta_of(R);
+            pl->grid = (u32)grid;
+            pl->lazy = lazy ? 1 : 0;
+            pl->nch = (u32)nch;
+            pl->global = 0;
+            pl->hybrid = 1;
+            pl->smem = hw * (meta_of(R) + cslot);
+            if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;
+            return true;
+        }
+    }
     if (sw + tm == 0) {
         // not on chip: points stay in global memory, one warp per cloud, worth it only when the batch keeps every SM
         // busy with many clouds (throughput from clouds in flight, HBM-bound); small batches go to the cluster kernels
@@ -535,6 +598,7 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         pl->lazy = lazy ? 1 : 0;
         pl->nch = (u32)nch;
         pl->global = 1;
+        pl->hybrid = 0;
         pl->smem = nwg * meta_of(R);
         const size_t gmax = (size_t)n_sms;   // spread over every SM before stacking warps
         pl->grid = (u32)(B < gmax ? B : gmax);
@@ -605,6 +669,7 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     a.meta_bytes = pl.meta_bytes;
     a.R = pl.rs;
     a.lazy = pl.lazy;
+    a.hybrid = pl.hybrid;
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;

@@ -85,6 +85,7 @@ def test_vanilla_vs_oracle(n, d, k, s, oracle):
 KD_SHAPES = [  # n, d, k, h, start
     (2, 3, 2, 1, 0), (64, 3, 20, 2, 1), (64, 3, 64, 6, 63), (1000, 3, 100, 3, 7), (4096, 3, 1024, 7, 3),
     (4096, 6, 512, 5, 5), (5000, 2, 300, 4, 1), (3000, 8, 200, 6, 0), (777, 1, 200, 3, 4), (4096, 3, 200, 12, 0),
+    (16384, 3, 700, 6, 11), (15500, 3, 300, 5, 2), (13000, 3, 400, 7, 1), (9000, 6, 300, 5, 4),
     (50000, 3, 4096, 7, 0), (100000, 3, 2000, 9, 0), (100000, 6, 1000, 9, 0), (300000, 4, 1000, 8, 9),
 ]
 
@@ -129,7 +130,7 @@ def test_async_batches_and_cluster_sizes(oracle):
 
 
 @pytest.mark.parametrize("env", [{"FPS_B200_WARP_GLOBAL_MINB": "1"}, {"FPS_B200_DIST": "1"}, {"FPS_B200_WARP_LAZY": "0"},
-                                 {"FPS_B200_WARP_TMEM": "0"}])
+                                 {"FPS_B200_WARP_TMEM": "0"}, {"FPS_B200_WARP_HYBRID": "1"}])
 def test_alternative_samplers(env, oracle):
     """every kd-line sampler must give the reference's indices, not only the one the planner prefers: the
     one-warp-per-cloud kernel over global memory (big batches), the distributed-bucket cluster kernel (opt-in),
@@ -137,8 +138,16 @@ def test_alternative_samplers(env, oracle):
     os.environ.update(env)
     try:
         want_plan = {"FPS_B200_WARP_GLOBAL_MINB": "kdline_warpg_kernel", "FPS_B200_DIST": "kdline_dist_kernel",
-                     "FPS_B200_WARP_LAZY": "eager", "FPS_B200_WARP_TMEM": "tmem 0"}[next(iter(env))]
+                     "FPS_B200_WARP_LAZY": "eager", "FPS_B200_WARP_TMEM": "tmem 0", "FPS_B200_WARP_HYBRID": "hybrid"}[next(iter(env))]
         big = next(iter(env)) in ("FPS_B200_WARP_GLOBAL_MINB", "FPS_B200_DIST")
+        if next(iter(env)) == "FPS_B200_WARP_HYBRID":   # only clouds between the shared-memory and the TMEM limit
+            for n, d, k, h, s, gen in [(16384, 3, 700, 7, 11, "u"), (15500, 3, 300, 5, 2, "g"), (16000, 3, 400, 6, 0, "l")]:
+                pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=37),
+                      "l": lambda: synth.lidar(n, n)}[gen]()
+                got = capi.kdline(pc, k, h, s)
+                assert want_plan in capi.last_plan(), capi.last_plan()
+                np.testing.assert_array_equal(got, oracle.kdline(pc, k, h, s), err_msg=capi.last_plan())
+            return
         shapes = [(30000, 3, 900, 7, 5, "u"), (20000, 6, 500, 6, 0, "u"), (40000, 2, 800, 5, 3, "g"), (50000, 1, 700, 5, 1, "g"),
                   (25000, 3, 600, 7, 2, "l")] if big else \
                  [(4096, 3, 1024, 5, 0, "u"), (3000, 6, 500, 5, 7, "u"), (5000, 2, 700, 7, 1, "g"), (4096, 3, 600, 6, 9, "l")]
