@@ -142,7 +142,9 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_async_kernel(AsyncArgs a) {
     ATab<DIM> *tab = reinterpret_cast<ATab<DIM> *>(bound + 2 * 32);
     u32 *issued = reinterpret_cast<u32 *>(tab + 2);
     u32 *done = issued + 16;
-    ARes<DIM> *res = reinterpret_cast<ARes<DIM> *>(done + 16);
+    u32 *rankv = done + 16;                                                   // [32] candidate ranks (atomic partial counts)
+    unsigned short *ptab = reinterpret_cast<unsigned short *>(rankv + 32);   // [512] pair p -> i | j << 8
+    ARes<DIM> *res = reinterpret_cast<ARes<DIM> *>(ptab + 512);
     float *bsnd = reinterpret_cast<float *>(res + S);
     float *bmc = bsnd + S;
     float *pendc = bmc + (size_t)DIM * S;
@@ -153,7 +155,12 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_async_kernel(AsyncArgs a) {
 
     // ---- one-time mailbox setup; generation counters then run across all clouds of this cluster -------------
     if (rank == 0) {
-        for (u32 i = tid; i < 32; i += T) issued[i] = 0;  // issued[16] + done[16]
+        for (u32 i = tid; i < 64; i += T) issued[i] = 0;  // issued[16] + done[16] + rankv[32]
+        for (u32 p = tid; p < 496; p += T) {
+            u32 j = 1;
+            while ((j + 1) * j / 2 <= p) ++j;
+            ptab[p] = (unsigned short)((p - j * (j - 1) / 2) | (j << 8));
+        }
         for (u32 b = tid; b < S; b += T) res[b].ch[0] = make_uint4(0, 0, 0, 0);
     } else if (tid < A_RING) {
         mbar_init(smem_u32(&bars[tid]), 1);  // one arrival per job: the coordinator's remote arrive.expect_tx
@@ -397,39 +404,54 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_async_kernel(AsyncArgs a) {
 #pragma unroll 1
                     for (u32 r = 0; r <= CPW; ++r) {
                         const u64 wk = warp_max_key(kk);
-                        const u32 src = __ffs(__ballot_sync(FULL, kk == wk)) - 1;
                         if (r == 0) wthr = __uint_as_float((u32)(wk >> 32));
-                        if (lane == 0) {
-                            if (r < CPW) {
-                                ACand &e = cand[par * A_NC + warp * CPW + r];
+                        // the lane holding the key publishes it itself (EXACT keys are unique; INFLIGHT keys may repeat:
+                        // the lanes then write the same key, and an INFLIGHT candidate only ever blocks what sorts behind it)
+                        const bool me = kk == wk && wk != 0ull;
+                        if (r < CPW) {
+                            ACand &e = cand[par * A_NC + warp * CPW + r];
+                            if (me) {
                                 e.key = wk;
-                                e.bucket = warp * 32 + src;
-                            } else {
-                                bound[par * 32 + warp] = wk;
+                                e.bucket = warp * 32 + lane;
+                            } else if (wk == 0ull && lane == 0) {
+                                e.key = 0ull;
+                                e.bucket = 0;
                             }
+                        } else if (lane == 0) {
+                            bound[par * 32 + warp] = wk;
                         }
-                        if (lane == src) kk = 0ull;
+                        if (me) kk = 0ull;
                     }
                     c1 = clock64();
+                    bar_sync_id(1, T);
+                    // ---- phase B0, everybody: lane l of warp w counts the candidates of warp w sorting in front of l ----
+                    {
+                        const u32 NCAND = NW * CPW;
+                        if (lane < NCAND) {
+                            const u64 myk = cand[par * A_NC + lane].key;
+                            u32 cnt = 0;
+#pragma unroll 1
+                            for (u32 m = warp * CPW; m < warp * CPW + CPW; ++m) {
+                                const u64 ok = cand[par * A_NC + m].key;
+                                cnt += ((ok > myk) | ((ok == myk) & (m < lane))) ? 1u : 0u;
+                            }
+                            if (cnt) atomicAdd(&rankv[lane], cnt);
+                        }
+                    }
                     if (warp != 0) {
-                        bar_arrive_id(1, T);
+                        bar_arrive_id(4, T);
                     } else {
-                        bar_sync_id(1, T);
+                        bar_sync_id(4, T);
                         c2 = clock64();
-                        // ---- phase B1, warp 0: sort the candidates (lane l ranks candidate l), publish the table ----
+                        // ---- phase B1, warp 0: publish the table in sorted order ------------------------------------------
                         const bool in = lane < NW * CPW;
                         const u64 myk = in ? cand[par * A_NC + lane].key : 0ull;
                         const u32 myb = in ? cand[par * A_NC + lane].bucket : 0u;
                         const u64 bd = warp_max_key(lane < NW ? bound[par * 32 + lane] : 0ull);
                         const u32 khi = (u32)(myk >> 32), klo = (u32)myk;
-                        // rank = number of candidates in front of mine; all 32 keys come from shared memory as
-                        // broadcast loads, compared branch-free so the loads pipeline
-                        u32 rank = 0;
-#pragma unroll
-                        for (u32 m = 0; m < 32; ++m) {
-                            const u64 ok = cand[par * A_NC + m].key;
-                            rank += ((ok > myk) | ((ok == myk) & (m < lane))) ? 1u : 0u;
-                        }
+                        // lanes beyond the candidates (key 0, never eligible) take the ranks behind them
+                        const u32 rank = in ? rankv[lane] : lane;
+                        if (in) rankv[lane] = 0;
                         ATab<DIM> &Tw = tab[par];
                         const bool elig = myk != 0ull && klo != A_MARK && myk > bd;
                         const u32 inel = __reduce_or_sync(FULL, elig ? 0u : (1u << rank));
@@ -453,10 +475,8 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_async_kernel(AsyncArgs a) {
                 if (L0 > 1) {
 #pragma unroll 1
                     for (u32 p = tid; p < NPAIR; p += T) {
-                        u32 j = (u32)((1.0f + sqrtf(1.0f + 8.0f * (float)p)) * 0.5f);
-                        while (j * (j - 1) / 2 > p) --j;
-                        while ((j + 1) * j / 2 <= p) ++j;
-                        const u32 i = p - j * (j - 1) / 2;
+                        const u32 ij = ptab[p];
+                        const u32 i = ij & 255u, j = ij >> 8;
                         if (j < L0) {
                             float Pi[DIM], Pj[DIM];
 #pragma unroll
@@ -560,7 +580,7 @@ size_t kd_region_bytes(size_t n, size_t dim, size_t h) {
 
 template <int DIM>
 static size_t async_smem(size_t S, size_t R) {
-    const size_t coord = sizeof(ACand) * 2 * A_NC + 2 * 32 * 8 + sizeof(ATab<DIM>) * 2 + 32 * 4 + sizeof(ARes<DIM>) * S +
+    const size_t coord = sizeof(ACand) * 2 * A_NC + 2 * 32 * 8 + sizeof(ATab<DIM>) * 2 + 32 * 4 + 32 * 4 + 512 * 2 + sizeof(ARes<DIM>) * S +
                          S * 4 + (size_t)DIM * S * 4 + R * DIM * S * 4;
     const size_t work = sizeof(AJob<DIM>) * A_RING + A_RING * 8 + 32 * 8 + 32 * 4;
     return (coord > work ? coord : work) + 16;
