@@ -22,10 +22,10 @@ EXT = os.path.join(HERE, "_fpsample" + (sysconfig.get_config_var("EXT_SUFFIX") o
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-    "-fmad=false",           # bit-exact parity: no FMA contraction anywhere (the kernels also use *_rn)
+    "-fmad=false", *os.environ.get("FPS_NVCC_EXTRA", "").split(),  # bit-exact parity: no FMA contraction anywhere (the kernels also use *_rn)
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
-CU = ["vanilla.cu", "kdline.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_dist.cu", "kdbuild.cu", "capi.cu"]
+CU = ["vanilla.cu", "kdline.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_dist.cu", "kdline_grid.cu", "kdbuild.cu", "capi.cu"]
 HDR = ["common.cuh", "kdcommon.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
 
 

@@ -242,8 +242,9 @@ struct KdLayout {
     AsyncPlan ap;
     WarpPlan wp;
     DistPlan dp;
-    bool async, gridbuild, warp, dist;
-    size_t region_off, region_stride, aux_off, counter_off, total;
+    GridPlan gp;
+    bool async, gridbuild, warp, dist, grid;
+    size_t region_off, region_stride, aux_off, counter_off, pub_off, total;
 };
 
 // fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
@@ -251,11 +252,13 @@ struct KdLayout {
 static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L) {
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
-    L->region_off = L->region_stride = L->aux_off = L->counter_off = 0;
-    L->gridbuild = false;
+    L->region_off = L->region_stride = L->aux_off = L->counter_off = L->pub_off = 0;
+    L->gridbuild = L->grid = L->dist = L->async = false;
     L->total = L->pl.ws_bytes;
     // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
-    L->warp = !build_only && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
+    bool force_grid = false;   // tests force the whole-GPU sampler onto clouds the planner would keep on one SM
+    if (const char *e = getenv("FPS_B200_GRID")) force_grid = atoi(e) == 1;
+    L->warp = !build_only && !force_grid && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {
         L->async = false;
         L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
@@ -266,9 +269,11 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     }
     // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
     // (kdline_async.cu) covers what is left (2^h > 512 buckets)
-    L->dist = !build_only && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
-    L->async = !build_only && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
-    if (L->async || L->dist) {
+    // one huge cloud: the whole GPU samples it, points in shared memory, batched picks (kdline_grid.cu)
+    L->grid = !build_only && (force_grid || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp);
+    L->dist = !build_only && !L->grid && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
+    L->async = !build_only && !L->grid && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
+    if (L->async || L->dist || L->grid) {
         // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
         L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
         if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
@@ -276,6 +281,10 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         L->region_stride = kd_region_bytes(n, dim, h);
         L->aux_off = L->region_off + B * L->region_stride;
         L->total = L->aux_off + (L->gridbuild ? B * kd_gridbuild_aux_bytes(n, dim, h) : 0);
+        if (L->grid) {
+            L->pub_off = (L->total + 255) & ~(size_t)255;
+            L->total = L->pub_off + kd_grid_pub_bytes(dim);
+        }
     }
     return cudaSuccess;
 }
@@ -316,6 +325,25 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
                               reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
                               (u32)dim, (u32)k, (u32)h, st));
+        tl_phase.mark(2, st);
+        return FPS_OK;
+    }
+    if (L.grid) {
+        a.region = static_cast<unsigned char *>(ws) + L.region_off;
+        a.region_stride = L.region_stride;
+        tl_phase.mark(0, st);
+        set_plan("%s + kdline_grid_kernel<DIM=%d> clouds=%zu grid=%u threads=1024 points/thread=%u candidates/round<=%u smem=%zu "
+                 "region/cloud=%zu",
+                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.gp.dimp, B,
+                 L.gp.G, L.gp.ppt, L.gp.ecap, L.gp.smem, L.region_stride);
+        if (L.gridbuild)
+            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
+                                   (u32)n, (u32)dim, (u32)h, st));
+        else
+            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        tl_phase.mark(1, st);
+        CK(launch_kdline_grid(L.gp, a.region, a.region_stride, d_starts, d_out, static_cast<unsigned char *>(ws) + L.pub_off,
+                              (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h, st));
         tl_phase.mark(2, st);
         return FPS_OK;
     }
@@ -516,6 +544,8 @@ int fps_b200_debug_counters(uint64_t *out16) {
         CK(warp_debug_counters(reinterpret_cast<u64 *>(out16)));
     else if (getenv("FPS_B200_DBG_BUILD"))
         CK(kb_debug_counters(reinterpret_cast<unsigned long long *>(out16)));
+    else if (getenv("FPS_B200_DBG_GRID"))
+        CK(grid_debug_counters(reinterpret_cast<u64 *>(out16)));
     else if (getenv("FPS_B200_DBG_DIST"))
         CK(dist_debug_counters(reinterpret_cast<u64 *>(out16)));
     else

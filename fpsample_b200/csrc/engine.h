@@ -110,6 +110,18 @@ bool plan_kdline_dist(size_t n, size_t dim, size_t h, size_t B, int n_sms, DistP
 cudaError_t launch_kdline_dist(const DistPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
 
+// ---- kd-line, one huge cloud on the whole GPU: points in shared memory, batched picks per grid-wide exchange (kdline_grid.cu) --
+struct GridPlan {
+    int dimp;
+    u32 ppt, G, ecap;
+    size_t smem;
+};
+size_t kd_grid_pub_bytes(size_t dim);
+bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl);
+cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
+                               unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
+cudaError_t grid_debug_counters(u64 *out16);
+
 // ---- kd-line build with the whole grid per level (kdbuild.cu), into the same per-cloud regions -------------
 size_t kd_gridbuild_aux_bytes(size_t n, size_t dim, size_t h);
 cudaError_t launch_kd_gridbuild(const float *pts, unsigned char *region, size_t region_stride, unsigned char *aux,

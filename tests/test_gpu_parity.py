@@ -167,6 +167,30 @@ def test_alternative_samplers(env, oracle):
             os.environ.pop(k_, None)
 
 
+@pytest.mark.parametrize("n,d,k,h,s,gen", [(300000, 3, 5000, 9, 0, "u"), (270001, 3, 3000, 8, 77, "l"), (150000, 3, 150000, 7, 3, "g"),
+                                           (65536, 2, 4000, 6, 1, "g"), (50000, 6, 2500, 7, 9, "u"), (9000, 1, 9000, 5, 0, "g"),
+                                           (200000, 4, 2000, 10, 5, "u"), (40000, 8, 1200, 6, 2, "u")])
+def test_grid_sampler(n, d, k, h, s, gen, oracle):
+    """the whole-GPU sampler for one huge cloud (kdline_grid_kernel: points in shared memory, a batch of picks per
+    grid-wide exchange) forced onto smaller clouds too: ties, duplicates (k = n drives every distance to 0), odd
+    sizes, every padded dimension."""
+    os.environ["FPS_B200_GRID"] = "1"
+    try:
+        pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=23),
+              "l": lambda: synth.lidar(n, n)}[gen]()
+        got = capi.kdline(pc, k, h, s)
+        assert "kdline_grid_kernel" in capi.last_plan(), capi.last_plan()
+        np.testing.assert_array_equal(got, oracle.kdline(pc, k, h, s), err_msg=capi.last_plan())
+        if n <= 65536:   # a batch runs cloud after cloud in one launch
+            pcs = np.stack([pc, pc[::-1].copy(), synth.uniform(n, n, d)])
+            gb = capi.kdline_batch(pcs, min(k, 500), h, [s, 0, 1], devices=[0])
+            assert "kdline_grid_kernel" in capi.last_plan(), capi.last_plan()
+            for b in range(3):
+                np.testing.assert_array_equal(gb[b], oracle.kdline(pcs[b], min(k, 500), h, [s, 0, 1][b]))
+    finally:
+        os.environ.pop("FPS_B200_GRID", None)
+
+
 def test_unaligned_and_strided_inputs(oracle):
     buf = synth.uniform(3, 4097 * 3 + 1, 1).ravel()
     pc = buf[1:1 + 4097 * 3].reshape(4097, 3)           # base address 4 bytes off any 16-byte boundary
@@ -285,6 +309,7 @@ def test_cfg3_batch_64x16384_h7(oracle):
 def test_cfg4_single_1m_to_64k_h9(gen, oracle, golden):
     pc = synth.uniform(5, 2**20, 3) if gen == "uniform" else synth.lidar(6, 2**20)
     got = capi.kdline(pc, 65536, 9, 0)
+    assert "kdline_grid_kernel" in capi.last_plan(), capi.last_plan()
     np.testing.assert_array_equal(got, golden["G5_kd_h9" if gen == "uniform" else "G6_kd_h9"])
     assert len(np.unique(got)) == 65536
 
