@@ -96,23 +96,6 @@ __device__ __forceinline__ void bar_sync_named(u32 id, u32 nthreads) {
 __device__ __forceinline__ float f4get(const float4 &v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
 __device__ __forceinline__ u64 key_max(u64 a, u64 b) { return a > b ? a : b; }
 
-// the slice's largest key below `last` (slow path of the re-selection, kept out of line: the round loop must stay small)
-__device__ __noinline__ u64 grid_rescan(const float4 *pvl, u32 NU, u32 p0, u64 last) {
-    u64 best = 0ull;
-#pragma unroll 1
-    for (u32 u = 0; u < NU; ++u) {
-        const float4 v = pvl[u * 32u];
-        const u32 l0 = p0 + u * 128u;
-#pragma unroll
-        for (int e4 = 0; e4 < 4; ++e4) {
-            const float x = f4get(v, e4);
-            const u64 key = x < 0.0f ? 0ull : make_key(x, G_LOW - (l0 + e4));
-            if (key < last && key > best) best = key;
-        }
-    }
-    return warp_max_key(best);
-}
-
 template <int DIM>
 __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -128,8 +111,8 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     float4 *pts = reinterpret_cast<float4 *>(smem_raw);                         // [DIM + 1][PCQ]
     u64 *gk = reinterpret_cast<u64 *>(pts + (size_t)(DIM + 1) * PCQ);           // [G][G_NK] gathered keys
     u64 *wtop = gk + (size_t)G_MAXG * G_NK;                                     // [G_W][4]: 2 keys, bound, pad
-    u64 *ekey = wtop + G_W * 4;                                                 // [3][G_ECAP]
-    u64 *red = ekey + 3 * G_ECAP;                                               // [8][4]
+    u64 *ekey = wtop + G_W * 4;                                                 // [G_ECAP]
+    u64 *red = ekey + G_ECAP;                                               // [8][4]
     u32 *tpos = reinterpret_cast<u32 *>(red + 32);                              // [G_ECAP]
     float *tval = reinterpret_cast<float *>(tpos + G_ECAP);                     // [G_ECAP]
     float *tc = tval + G_ECAP;                                                  // [DIM][G_ECAP]
@@ -138,10 +121,11 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     u32 *misc = reinterpret_cast<u32 *>(cbox + 2 * DIM);                        // [16]
     u32 *wflag = misc + 16;                                                     // [16] conflict flag per window
     u32 *lw = wflag + 16;                                                       // [2][8] lowered-candidate bit words
-    u32 *rowany = lw + 16;                                                      // [G_ECAP]
+    u32 *pickw = lw + 16;                                                       // [8] pick mask words, [8] their exclusive prefix counts
+    u32 *rowany = pickw + 16;                                                      // [G_ECAP]
     u32 *conf = rowany + G_ECAP;                                                // [G_ECAP][8] conflict bits
     u32 *cum = conf + G_ECAP * 8;                                               // [S + 1] first slice of every leaf
-    enum { M_NREL = 0, M_STOP = 1, M_CUR = 2, M_E0 = 4 };
+    enum { M_NREL = 0, M_STOP = 1, M_J = 2, M_E0 = 4 };
 
     float4 *pv = pts + (size_t)DIM * PCQ;   // running distances; padding slots hold -1 (never a candidate)
 
@@ -237,12 +221,11 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
         }
         float smax = 0.0f;   // exact maximum of the slice (warp-uniform)
 
-        // The warp's 2 largest keys + the third (its bound).  One pass: every lane keeps its two best (ascending
-        // positions, strict '>': the lowest position wins a tie), the warp then pops three times.  A lane that is
-        // popped twice no longer knows its next value: the (rare) slow path rescans for every key.
+        // The warp's 2 largest keys + the third (its bound).  One pass: every lane keeps its three best (ascending
+        // positions, strict '>': the lowest position wins a tie), the warp then pops three times.
         auto reselect = [&]() {
-            float v1 = -1.0f, v2 = -1.0f;
-            u32 p1 = 0, p2 = 0;
+            float v1 = -1.0f, v2 = -1.0f, v3 = -1.0f;
+            u32 p1 = 0, p2 = 0, p3 = 0;
 #pragma unroll 1
             for (u32 u = 0; u < NU; ++u) {
                 const float4 v = pv[(warp * NU + u) * 32u + lane];
@@ -250,15 +233,17 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
 #pragma unroll
                 for (int e4 = 0; e4 < 4; ++e4) {
                     const float x = f4get(v, e4);
-                    const bool g1 = x > v1, g2 = x > v2;
+                    const bool g1 = x > v1, g2 = x > v2, g3 = x > v3;
+                    v3 = g2 ? v2 : (g3 ? x : v3);
+                    p3 = g2 ? p2 : (g3 ? l0 + e4 : p3);
                     v2 = g1 ? v1 : (g2 ? x : v2);
                     p2 = g1 ? p1 : (g2 ? l0 + e4 : p2);
                     v1 = g1 ? x : v1;
                     p1 = g1 ? l0 + e4 : p1;
                 }
             }
-            u64 k1 = v1 < 0.0f ? 0ull : make_key(v1, G_LOW - p1), k2 = v2 < 0.0f ? 0ull : make_key(v2, G_LOW - p2);
-            u32 pops = 0;
+            u64 k1 = v1 < 0.0f ? 0ull : make_key(v1, G_LOW - p1), k2 = v2 < 0.0f ? 0ull : make_key(v2, G_LOW - p2),
+                k3 = v3 < 0.0f ? 0ull : make_key(v3, G_LOW - p3);
             u64 res[3];
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
@@ -266,15 +251,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 res[e] = wk;
                 if (e < 2 && wk != 0ull && k1 == wk) {
                     k1 = k2;
-                    k2 = 0ull;
-                    ++pops;
+                    k2 = k3;
+                    k3 = 0ull;
                 }
-            }
-            // a lane popped twice holds unknown values below its second key: the third key may be one of them -> rescan
-            if (__any_sync(FULL, pops >= 2)) {
-                res[0] = grid_rescan(pv + warp * NU * 32u + lane, NU, wpos0 + lane * 4u, ~0ull);
-                res[1] = res[0] ? grid_rescan(pv + warp * NU * 32u + lane, NU, wpos0 + lane * 4u, res[0]) : 0ull;
-                res[2] = res[1] ? grid_rescan(pv + warp * NU * 32u + lane, NU, wpos0 + lane * 4u, res[1]) : 0ull;
             }
             if (lane < 3) wtop[warp * 4 + lane] = lane == 0 ? res[0] : lane == 1 ? res[1] : res[2];
             smax = __uint_as_float((u32)(res[0] >> 32));
@@ -397,7 +376,6 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             __syncwarp();   // lanes leave the spin loop one by one: converge before the warp collectives below
             if (tid < 16) wflag[tid] = 0;
-            if (tid < 3) misc[M_E0 + tid] = 0;
             if (tid == 0) {
                 misc[M_NREL] = 0;
             }
@@ -407,68 +385,67 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             // A candidate is eligible when it sorts above EVERY CTA's bound.  With the first M' keys of every CTA as
             // candidates, CTA c's bound is max(its slice bound, its key[M']); M' = 8, 4 or 1: the largest that leaves at
             // most ECAP candidates (three lists are built at once).
-            const u32 NWG = (G + 31) >> 5;   // warps holding CTAs
-            long long e1 = c3, e2 = c3;
+            const u32 NWG = (G + 31) >> 5;   // warps holding CTAs: thread c < G looks after CTA c's ten keys
+            long long d1 = c3;
             if (warp < NWG) {
-                u64 b8 = 0ull, b4 = 0ull, b1 = 0ull;
-                if (tid < G) {
-                    const u64 *kc = gk + tid * G_NK;
-                    const u64 wb = kc[G_M + 1];
-                    b8 = key_max(wb, kc[8]);
-                    b4 = key_max(wb, kc[4]);
-                    b1 = key_max(wb, kc[1]);
-                }
-                b8 = warp_max_key(b8);
-                b4 = warp_max_key(b4);
-                b1 = warp_max_key(b1);
-                e1 = GCLK();
+                u64 kc[G_NK];
+#pragma unroll
+                for (u32 e = 0; e < G_NK; ++e) kc[e] = tid < G ? gk[tid * G_NK + e] : 0ull;
+                const u64 wb = kc[G_M + 1];
+                const u64 b8 = warp_max_key(key_max(wb, kc[8])), b4 = warp_max_key(key_max(wb, kc[4])),
+                          b1 = warp_max_key(key_max(wb, kc[1]));
                 if (lane == 0) {
                     red[warp * 4] = b8;
                     red[warp * 4 + 1] = b4;
                     red[warp * 4 + 2] = b1;
                 }
-                e2 = GCLK();
-            }
-            __syncthreads();
-            const long long d1 = GCLK();
-            u64 Bd8 = 0ull, Bd4 = 0ull, Bd1 = 0ull;
+                bar_sync_named(2, NWG * 32);
+                d1 = GCLK();
+                u64 Bd8 = 0ull, Bd4 = 0ull, Bd1 = 0ull;
 #pragma unroll 1
-            for (u32 w = 0; w < NWG; ++w) {
-                Bd8 = key_max(Bd8, red[w * 4]);
-                Bd4 = key_max(Bd4, red[w * 4 + 1]);
-                Bd1 = key_max(Bd1, red[w * 4 + 2]);
-            }
+                for (u32 w = 0; w < NWG; ++w) {
+                    Bd8 = key_max(Bd8, red[w * 4]);
+                    Bd4 = key_max(Bd4, red[w * 4 + 1]);
+                    Bd1 = key_max(Bd1, red[w * 4 + 2]);
+                }
+                // the eligible keys of a CTA are a prefix of its descending list: three counts, packed into one word
+                u32 c8 = 0, c4 = 0;
+#pragma unroll
+                for (u32 e = 0; e < G_M; ++e) {
+                    c8 += kc[e] > Bd8;
+                    if (e < 4) c4 += kc[e] > Bd4;
+                }
+                const u32 c1 = kc[0] > Bd1;
+                const u32 mine = c8 | (c4 << 11) | (c1 << 22);   // every total is below 2^11
+                u32 inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(FULL, inc, o);
+                    if (lane >= (u32)o) inc += y;
+                }
+                u32 *tot = reinterpret_cast<u32 *>(red + 24);   // [8] warp totals (red[0..19] hold the bounds)
+                if (lane == 31) tot[warp] = inc;
+                bar_sync_named(2, NWG * 32);
+                u32 all = 0, before = 0;
 #pragma unroll 1
-            for (u32 idx0 = 0; idx0 < G * G_M; idx0 += G_T) {   // one published key per thread
-                if (idx0 + warp * 32 >= G * G_M) break;         // warp-uniform
-                const u32 idx = idx0 + tid;
-                u64 kk = 0ull;
-                u32 e = 0;
-                if (idx < G * G_M) {
-                    e = idx & (G_M - 1);
-                    kk = gk[(idx / G_M) * G_NK + e];
+                for (u32 w = 0; w < NWG; ++w) {
+                    const u32 x = tot[w];
+                    all += x;
+                    before += w < warp ? x : 0u;
                 }
-                const bool f8 = kk > Bd8, f4 = kk > Bd4 && e < 4, f1 = kk > Bd1 && e < 1;
-                const u32 m8 = __ballot_sync(FULL, f8), m4 = __ballot_sync(FULL, f4), m1 = __ballot_sync(FULL, f1);
-                u32 o8 = 0, o4 = 0, o1 = 0;
-                if (lane == 0) {   // three independent atomics in flight
-                    if (m8) o8 = atomicAdd(&misc[M_E0], (u32)__popc(m8));
-                    if (m4) o4 = atomicAdd(&misc[M_E0 + 1], (u32)__popc(m4));
-                    if (m1) o1 = atomicAdd(&misc[M_E0 + 2], (u32)__popc(m1));
-                }
-                const u32 lt = (1u << lane) - 1u;
-                o8 = __shfl_sync(FULL, o8, 0) + __popc(m8 & lt);
-                o4 = __shfl_sync(FULL, o4, 0) + __popc(m4 & lt);
-                o1 = __shfl_sync(FULL, o1, 0) + __popc(m1 & lt);
-                if (f8 && o8 < G_ECAP) ekey[o8] = kk;
-                if (f4 && o4 < G_ECAP) ekey[G_ECAP + o4] = kk;
-                if (f1 && o1 < G_ECAP) ekey[2 * G_ECAP + o1] = kk;
+                const u32 E8 = all & 0x7ffu, E4 = (all >> 11) & 0x7ffu;
+                const u32 vs = E8 <= ECAP ? 0u : (E4 <= ECAP ? 1u : 2u);
+                const u32 shf = vs * 11u;
+                const u32 cnt = (mine >> shf) & 0x7ffu, off = ((before + inc - mine) >> shf) & 0x7ffu;
+#pragma unroll
+                for (u32 e = 0; e < G_M; ++e)
+                    if (e < cnt && off + e < G_ECAP) ekey[off + e] = kc[e];
+                if (tid == 0) misc[M_E0] = (all >> shf) & 0x7ffu;
             }
             __syncthreads();
             const long long d2 = GCLK();
-            const u32 vsel = misc[M_E0] <= ECAP ? 0u : (misc[M_E0 + 1] <= ECAP ? 1u : 2u);
-            const u32 E = min(misc[M_E0 + vsel], G_ECAP);
-            const u64 *ek = ekey + vsel * G_ECAP;
+            const u32 E = min(misc[M_E0], G_ECAP);
+            const u64 *ek = ekey;
             // rank by counting: 1024 / E2 adjacent lanes per candidate (E2 = E rounded up to a power of two >= 32); the
             // candidate's coordinates are fetched from the region (L2) meanwhile
             {
@@ -528,9 +505,12 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 }
                 if (lane == 0) rowany[j] = any;
             }
+            const long long g1 = GCLK();
             if (tid < 16) lw[tid] = 0;
             if (tid == 0) misc[M_STOP] = E;
             __syncthreads();
+            long long g2 = g1, g3 = g1;
+            u32 nit = 0;
             if (warp < 8) {   // E <= 256 candidates: one thread each, named barrier 1
                 const u32 j = tid;
                 const u32 nblk = (j + 31) >> 5;
@@ -551,9 +531,11 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     if (tid == 0) wflag[(it + 1) & 15] = 0;
                     bar_sync_named(1, 256);
                     cur ^= 1;
+                    ++nit;
                     if (!wflag[it & 15]) break;   // nothing changed: lw[cur] is the solution (uniform: written before the barrier)
                 }
                 // lw[cur] holds the lowered set
+                g2 = GCLK();
                 const bool low = j < E && ((lw[cur * 8 + warp] >> lane) & 1u);
                 if (j < E) {
                     u32 st = E;
@@ -586,20 +568,32 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     }
                     if (st < E) atomicMin(&misc[M_STOP], st);
                 }
-                if (tid == 0) misc[M_CUR] = cur;
+                g3 = GCLK();
+                bar_sync_named(1, 256);   // M_STOP is final
+                if (warp == 0) {          // picks = candidates before `stop` that are not lowered: mask words, their prefix counts
+                    const u32 stop = misc[M_STOP];
+                    u32 m = 0;
+                    if (lane < 8) {
+                        const u32 lim = stop > lane * 32 ? min(stop - lane * 32, 32u) : 0u;
+                        m = ~lw[cur * 8 + lane] & (lim == 32 ? 0xffffffffu : ((1u << lim) - 1u));
+                    }
+                    u32 inc = __popc(m);
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        const u32 y = __shfl_up_sync(FULL, inc, o);
+                        if (lane >= (u32)o) inc += y;
+                    }
+                    if (lane < 8) {
+                        pickw[lane] = m;
+                        pickw[8 + lane] = inc - __popc(m);
+                    }
+                    if (lane == 7) misc[M_J] = inc;
+                }
             }
             __syncthreads();
             const long long c5 = GCLK();
-            const u32 stop = misc[M_STOP];
-            const u32 *lwf = lw + misc[M_CUR] * 8;
             const bool allzero = tval[0] == 0.0f;   // every remaining distance is 0: the same position wins for ever
-            // picks = candidates before `stop` that are not lowered, in order; at most k - t of them
-            u32 J = 0;
-#pragma unroll
-            for (u32 w = 0; w < 8; ++w) {
-                const u32 lim = stop > w * 32 ? min(stop - w * 32, 32u) : 0u;
-                J += __popc(~lwf[w] & (lim == 32 ? 0xffffffffu : ((1u << lim) - 1u)));
-            }
+            u32 J = misc[M_J];
             if (allzero) J = 1;
             if (J > k - t) J = k - t;
             if (allzero) {
@@ -610,9 +604,8 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 }
                 t = k;
             } else {
-                if (tid < stop && !((lwf[tid >> 5] >> (tid & 31)) & 1u)) {
-                    u32 idx = __popc(~lwf[tid >> 5] & ((1u << (tid & 31)) - 1u));
-                    for (u32 w = 0; w < (tid >> 5); ++w) idx += __popc(~lwf[w]);
+                if (tid < G_ECAP && ((pickw[tid >> 5] >> (tid & 31)) & 1u)) {
+                    const u32 idx = pickw[8 + (tid >> 5)] + __popc(pickw[tid >> 5] & ((1u << (tid & 31)) - 1u));
                     if (idx < J) {
                         if (cta == 0) out[t + idx] = (u64)tpos[tid];
                         // picks that can touch this CTA at all (CTA box against the CTA maximum)
@@ -642,9 +635,10 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 dbg[9] += (u64)(d2 - d1);   // D: compaction
                 dbg[10] += (u64)(c4 - d2);  // D: rank + table
                 dbg[12] += E;
-                dbg[13] += (u64)(e1 - c3);
-                dbg[14] += (u64)(e2 - e1);
-                dbg[15] += (u64)(d1 - e2);
+                dbg[13] += (u64)(g1 - c4);   // E1 conflict matrix
+                dbg[14] += (u64)(g2 - g1);   // E2 fixed point
+                dbg[15] += (u64)(g3 - g2);   // E3 floors
+                dbg[11] += nit;
             }
 #endif
         }
@@ -673,11 +667,11 @@ static size_t grid_smem(int dimp, u32 ppt, size_t S) {
     const size_t pcq = (size_t)G_W * (ppt / 4) * 32;
     size_t b = (size_t)(dimp + 1) * pcq * 16;            // points
     b += (size_t)G_MAXG * G_NK * 8;                      // gathered keys
-    b += G_W * 4 * 8 + 3 * G_ECAP * 8 + 32 * 8;          // wtop, ekey, red
+    b += G_W * 4 * 8 + G_ECAP * 8 + 32 * 8;              // wtop, ekey, red
     b += (size_t)G_ECAP * 4 * 2;                         // tpos, tval
     b += (size_t)dimp * G_ECAP * 4 + G_ECAP * 4;         // tc, rel
     b += 2 * dimp * 4 + 16 * 4 + 16 * 4 + (S + 1) * 4;   // cbox, misc, wflag, cum
-    b += 16 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4;           // lw, rowany, conf
+    b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4;           // lw, pickw, rowany, conf
     return (b + 15) & ~(size_t)15;
 }
 

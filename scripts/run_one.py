@@ -39,7 +39,7 @@ if algo == "kdline" and "kdline_grid" in capi.last_plan():
     it = max(int(o[0]), 1)
     print("  grid dbg (CTA 0): rounds %d picks/round %.1f | cycles per round: apply+select %.0f merge+publish %.0f gather %.0f eligible+rank %.0f pairs %.0f out+rel %.0f = %.0f" % (
         o[0], o[1] / it, o[2] / it, o[3] / it, o[4] / it, o[5] / it, o[6] / it, o[7] / it, sum(int(x) for x in o[2:8]) / it))
-    print("     eligible+rank split: bounds %.0f compaction %.0f rank %.0f table %.0f | E/round %.1f | bounds: to-redux %.0f sts %.0f barrier %.0f" % (o[8] / it, o[9] / it, o[10] / it, o[11] / it, o[12] / it, o[13] / it, o[14] / it, o[15] / it))
+    print("     eligible+rank split: bounds %.0f compaction %.0f rank %.0f table %.0f | E/round %.1f | picks phase: conflict matrix %.0f fixed point %.0f (%.1f iterations) floors %.0f" % (o[8] / it, o[9] / it, o[10] / it, 0.0, o[12] / it, o[13] / it, o[14] / it, o[11] / it, o[15] / it))
 if algo == "kdline" and "async" in capi.last_plan():
     d = capi.debug_counters(); it = max(d["iterations"], 1)
     print("  dbg:", d, "| per iteration:", {k: round(v / it, 1) for k, v in d.items() if k.startswith("cyc")}, "picks/iter %.2f" % (d["picks"] / it))
