@@ -24,6 +24,8 @@ try:
         __version__,
         _bucket_fps_kdline_sampling,
         _bucket_fps_kdline_sampling_batch,
+        _bucket_fps_kdtree_sampling,
+        _bucket_fps_kdtree_sampling_batch,
         _device_count,
         _fps_sampling,
         _fps_sampling_batch,
@@ -96,6 +98,25 @@ def bucket_fps_kdline_sampling(pc: np.ndarray, n_samples: int, h: int,
     return _bucket_fps_kdline_sampling(pc, n_samples, h, start_idx)
 
 
+def bucket_fps_kdtree_sampling(pc: np.ndarray, n_samples: int,
+                               start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
+    """QuickFPS with the full kd tree (reference: src/fpsample/__init__.py:145-171).
+
+    As in the reference, start_idx addresses the POSITION in the array after the (full-depth) kd build permuted
+    it (src/wrapper.hpp:36-37), and distance ties go to the highest position (src/_ext/KDNode.h:41-46).
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pc.ndim == 2
+    n_pts, _ = pc.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    assert start_idx is None or 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    if isinstance(start_idx, list):
+        assert len(start_idx) <= n_samples, "len(start_idx) should be <= n_samples"
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    start_idx = get_start_idx(n_pts, start_idx)
+    return _bucket_fps_kdtree_sampling(pc, n_samples, start_idx)
+
+
 def _batch_start(start_idx, b: int, n_pts: int):
     if start_idx is None or isinstance(start_idx, int):
         if isinstance(start_idx, int):
@@ -138,6 +159,19 @@ def bucket_fps_kdline_sampling_batch(pcs: np.ndarray, n_samples: int, h: int,
                                              None if devices is None else list(devices))
 
 
+def bucket_fps_kdtree_sampling_batch(pcs: np.ndarray, n_samples: int,
+                                     start_idx: Optional[Union[int, Sequence[int]]] = None,
+                                     devices: Optional[Sequence[int]] = None) -> np.ndarray:
+    """QuickFPS full kd tree over a batch [B, N, D]; row b equals bucket_fps_kdtree_sampling(pcs[b], ...)."""
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pcs.ndim == 3
+    b, n_pts, _ = pcs.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    pcs = np.ascontiguousarray(pcs, dtype=np.float32)
+    return _bucket_fps_kdtree_sampling_batch(pcs, n_samples, _batch_start(start_idx, b, n_pts),
+                                             None if devices is None else list(devices))
+
+
 def _out_of_scope(name):
     def f(*a, **k):
         raise NotImplementedError(
@@ -148,7 +182,6 @@ def _out_of_scope(name):
 
 fps_npdu_sampling = _out_of_scope("fps_npdu_sampling")
 fps_npdu_kdtree_sampling = _out_of_scope("fps_npdu_kdtree_sampling")
-bucket_fps_kdtree_sampling = _out_of_scope("bucket_fps_kdtree_sampling")
 
 __all__ = [
     "__version__",
@@ -156,6 +189,7 @@ __all__ = [
     "bucket_fps_kdline_sampling",
     "fps_sampling_batch",
     "bucket_fps_kdline_sampling_batch",
+    "bucket_fps_kdtree_sampling_batch",
     "fps_npdu_sampling",
     "fps_npdu_kdtree_sampling",
     "bucket_fps_kdtree_sampling",

@@ -11,12 +11,15 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfps_b200.so")
 
-ALGO_VANILLA, ALGO_KDLINE = 0, 1
+ALGO_VANILLA, ALGO_KDLINE, ALGO_KDTREE = 0, 1, 2
 
 EXPORTS = {
     # name: (restype, argtypes)
     "fps_b200_vanilla": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 3 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "bucket_fps_kdline": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p]),
+    "bucket_fps_kdtree": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p]),
+    "fps_b200_kdtree_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "fps_b200_kdtree_batch_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "fps_b200_vanilla_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "fps_b200_kdline_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "fps_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int] + [ctypes.c_size_t] * 5),
@@ -120,6 +123,13 @@ def kdline(pc, k, h, start=0):
     return out
 
 
+def kdtree(pc, k, start=0):
+    pc = _f32(pc, 2)
+    out = np.empty(k, dtype=np.uint64)
+    _check("bucket_fps_kdtree", lib().bucket_fps_kdtree(pc.ctypes.data, pc.shape[0], pc.shape[1], k, start, out.ctypes.data))
+    return out
+
+
 def _starts(start, b):
     if start is None:
         return None
@@ -151,6 +161,18 @@ def kdline_batch(pcs, k, h, start=None, devices=None):
     return out
 
 
+def kdtree_batch(pcs, k, start=None, devices=None):
+    pcs = _f32(pcs, 3)
+    b, n, d = pcs.shape
+    st = _starts(start, b)
+    dv = None if devices is None else np.asarray(devices, dtype=np.int32)
+    out = np.empty((b, k), dtype=np.uint64)
+    _check("fps_b200_kdtree_batch", lib().fps_b200_kdtree_batch(
+        pcs.ctypes.data, b, n, d, k, None if st is None else st.ctypes.data, out.ctypes.data,
+        None if dv is None else dv.ctypes.data, 0 if dv is None else dv.size))
+    return out
+
+
 # ---- device-pointer entries (raw integer addresses, e.g. torch.Tensor.data_ptr()) -------------------------
 def workspace_bytes(algo, b, n, d, k, h=0) -> int:
     return int(lib().fps_b200_workspace_bytes(algo, b, n, d, k, h))
@@ -164,6 +186,11 @@ def vanilla_batch_dev(d_pts, b, n, d, k, d_start, d_out, d_ws, ws_bytes, stream=
 def kdline_batch_dev(d_pts, b, n, d, k, d_start, h, d_out, d_ws, ws_bytes, stream=0):
     _check("fps_b200_kdline_batch_dev", lib().fps_b200_kdline_batch_dev(
         d_pts, b, n, d, k, d_start or None, h, d_out, d_ws or None, ws_bytes, stream or None))
+
+
+def kdtree_batch_dev(d_pts, b, n, d, k, d_start, d_out, d_ws, ws_bytes, stream=0):
+    _check("fps_b200_kdtree_batch_dev", lib().fps_b200_kdtree_batch_dev(
+        d_pts, b, n, d, k, d_start or None, d_out, d_ws or None, ws_bytes, stream or None))
 
 
 def kdline_build_dev(d_pts, b, n, d, h, d_perm, d_leaf_lo, d_leaf_box, d_ws, ws_bytes, stream=0):

@@ -395,6 +395,45 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     return FPS_OK;
 }
 
+// ---- full kd tree (bucket_fps_kdtree_sampling): GPU build of the full permutation, vanilla kernels over the permuted rows ----
+struct KtLayout {
+    WsLayout v;
+    size_t region_off, region_stride, rows_off, vws_off, total;
+};
+static void kdtree_layout(size_t B, size_t n, size_t dim, int n_sms, KtLayout *L) {
+    vanilla_layout(B, n, dim, n_sms, &L->v);
+    L->region_off = 0;
+    L->region_stride = kdtree_region_bytes(n, dim);
+    L->rows_off = L->region_off + B * L->region_stride;
+    L->vws_off = (L->rows_off + B * n * dim * sizeof(float) + 255) & ~(size_t)255;
+    L->total = L->vws_off + L->v.total;
+}
+
+static int enqueue_kdtree(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts, u64 *d_out,
+                          void *ws, size_t ws_bytes, int n_sms, cudaStream_t st) {
+    KtLayout L;
+    kdtree_layout(B, n, dim, n_sms, &L);
+    if (!ws || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) {
+        set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", L.total, ws_bytes);
+        return FPS_ERR_WORKSPACE;
+    }
+    unsigned char *w = static_cast<unsigned char *>(ws);
+    float *rows = reinterpret_cast<float *>(w + L.rows_off);
+    tl_phase.mark(0, st);
+    CK(launch_kdtree_build(d_pts, w + L.region_off, L.region_stride, rows, (u32)B, (u32)n, (u32)dim, n_sms, st));
+    // positions: exact FPS over the permuted rows from POSITION start, ties to the highest position (KDNode.h:41-46)
+    PhaseTimer keep = tl_phase;   // the vanilla enqueue marks its own phases: keep ours
+    int rc = enqueue_vanilla(rows, B, n, dim, k, d_starts, 1, d_out, w + L.vws_off, L.v.total, n_sms, st);
+    if (rc) return rc;
+    std::string vplan = tl_plan;
+    CK(launch_kdtree_map(d_out, w + L.region_off, L.region_stride, (u32)B, (u32)n, (u32)k, (u32)dim, st));
+    tl_phase = keep;
+    tl_phase.mark(1, st);
+    tl_phase.mark(2, st);
+    set_plan("kdtree_build_kernel(full kd permutation, 1 CTA per cloud) + %s + kdtree_map_kernel", vplan.c_str());
+    return FPS_OK;
+}
+
 // ---- host-pointer shard on one device ------------------------------------------------------------------------------
 struct ShardJob {
     int algo;
@@ -438,6 +477,10 @@ static int run_shard(int dev, const ShardJob &j) {
             WsLayout L;
             vanilla_layout(nb, j.n, j.dim, cx->n_sms, &L);
             ws_need = L.total;
+        } else if (j.algo == FPS_ALGO_KDTREE) {
+            KtLayout L;
+            kdtree_layout(nb, j.n, j.dim, cx->n_sms, &L);
+            ws_need = L.total;
         } else {
             KdLayout L;
             CK(kd_layout(nb, j.n, j.dim, j.h, cx->n_sms, false, &L));
@@ -455,6 +498,9 @@ static int run_shard(int dev, const ShardJob &j) {
         if (j.algo == FPS_ALGO_VANILLA)
             rc = enqueue_vanilla(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.n_starts,
                                  static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
+        else if (j.algo == FPS_ALGO_KDTREE)
+            rc = enqueue_kdtree(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts,
+                                static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else
             rc = enqueue_kdline(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.h,
                                 static_cast<u64 *>(ln.out.p), nullptr, nullptr, nullptr, ln.ws.p, ln.ws.cap,
@@ -616,6 +662,57 @@ int bucket_fps_kdline(const float *raw_data, size_t n_points, size_t dim, size_t
     return run_batch(j, nullptr, 1);
 }
 
+int bucket_fps_kdtree(const float *raw_data, size_t n_points, size_t dim, size_t n_samples, size_t start_idx, size_t *out) {
+    // same order and codes as src/wrapper.hpp:105-111
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    if (start_idx >= n_points) {
+        set_err("start_idx %zu out of range (n=%zu)", start_idx, n_points);
+        return FPS_ERR_START;
+    }
+    int rc = check_common(raw_data, 1, n_points, dim, n_samples, out);
+    if (rc) return rc;
+    ShardJob j{FPS_ALGO_KDTREE, raw_data, 1, n_points, dim, n_samples, 0, &start_idx, 1, out};
+    return run_batch(j, nullptr, 1);
+}
+
+int fps_b200_kdtree_batch(const float *points, size_t B, size_t n, size_t dim, size_t k, const size_t *start, size_t *out,
+                          const int *devices, int n_devices) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    if (start)
+        for (size_t b = 0; b < B; ++b)
+            if (start[b] >= n) {
+                set_err("start[%zu]=%zu out of range (n=%zu)", b, start[b], n);
+                return FPS_ERR_START;
+            }
+    int rc = check_common(points, B, n, dim, k, out);
+    if (rc) return rc;
+    ShardJob j{FPS_ALGO_KDTREE, points, B, n, dim, k, 0, start, 1, out};
+    return run_batch(j, devices, n_devices);
+}
+
+int fps_b200_kdtree_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k, const uint64_t *d_start,
+                              uint64_t *d_out, void *d_workspace, size_t workspace_bytes, void *stream) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    int rc = check_common(d_points, B, n, dim, k, d_out);
+    if (rc) return rc;
+    int n_sms = n_sms_current(nullptr);
+    if (n_sms <= 0) {
+        set_err("current device is not a usable sm_100 device; there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    return enqueue_kdtree(d_points, B, n, dim, k, reinterpret_cast<const u64 *>(d_start), reinterpret_cast<u64 *>(d_out),
+                          d_workspace, workspace_bytes, n_sms, static_cast<cudaStream_t>(stream));
+}
+
 int fps_b200_vanilla_batch(const float *points, size_t B, size_t n, size_t dim, size_t k, const size_t *start,
                            size_t *out, const int *devices, int n_devices) {
     int rc = check_common(points, B, n, dim, k, out);
@@ -656,6 +753,12 @@ size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t
     if (algo == FPS_ALGO_VANILLA) {
         WsLayout L;
         vanilla_layout(B, n, dim, n_sms, &L);
+        return L.total;
+    }
+    if (algo == FPS_ALGO_KDTREE) {
+        if (dim > FPS_B200_MAX_KDLINE_DIM) return 0;
+        KtLayout L;
+        kdtree_layout(B, n, dim, n_sms, &L);
         return L.total;
     }
     if (dim > FPS_B200_MAX_KDLINE_DIM || check_kdline(n, dim, height)) return 0;

@@ -127,6 +127,13 @@ size_t kd_gridbuild_aux_bytes(size_t n, size_t dim, size_t h);
 cudaError_t launch_kd_gridbuild(const float *pts, unsigned char *region, size_t region_stride, unsigned char *aux,
                                 u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
 
+// ---- full kd tree (bucket_fps_kdtree_sampling): GPU build of the permutation, then the vanilla kernels (kdtree.cu) ----
+size_t kdtree_region_bytes(size_t n, size_t dim);
+cudaError_t launch_kdtree_build(const float *pts, unsigned char *region, size_t region_stride, float *rows, u32 B, u32 n,
+                                u32 dim, int n_sms, cudaStream_t st);
+cudaError_t launch_kdtree_map(u64 *out, const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 k, u32 dim,
+                              cudaStream_t st);
+
 void count_launch();
 
 }  // namespace fps

@@ -93,6 +93,34 @@ static py::array_t<size_t> kdline_py(farray points, size_t n_samples, size_t hei
     return out;
 }
 
+// src/lib.cpp:467-520
+static py::array_t<size_t> kdtree_py(farray points, size_t n_samples, py::object start_idx_obj) {
+    size_t start = 0;
+    if (py::isinstance<py::int_>(start_idx_obj)) {
+        start = start_idx_obj.cast<size_t>();
+    } else if (py::isinstance<py::array_t<size_t>>(start_idx_obj)) {
+        PyErr_SetString(PyExc_NotImplementedError, "Array of start indices not implemented yet");
+        throw py::error_already_set();
+    } else {
+        throw py::type_error("start_idx must be int or 1D numpy array of size_t");
+    }
+    if (points.ndim() != 2) throw py::value_error("points must be a 2D float32 array");
+    const size_t P = (size_t)points.shape(0), C = (size_t)points.shape(1);
+    if (C == 0) throw py::value_error("points must have at least one column");
+    if (start >= P) throw py::value_error("start_idx out of range");
+    if (n_samples == 0 || n_samples > P) throw py::value_error("n_samples must be in [1, num_points]");
+    py::array_t<size_t> out(n_samples);
+    int rc;
+    {
+        const float *src = points.data();
+        size_t *dst = out.mutable_data();
+        py::gil_scoped_release rel;
+        rc = bucket_fps_kdtree(src, P, C, n_samples, start, dst);
+    }
+    if (rc != 0) raise_rc("bucket_fps_kdtree", rc);
+    return out;
+}
+
 // ---- batched entries (new) -----------------------------------------------------------------------------
 static std::vector<size_t> batch_starts(py::object start_obj, size_t B, size_t P) {
     std::vector<size_t> st;
@@ -131,10 +159,13 @@ static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, s
         py::gil_scoped_release rel;
         if (algo == FPS_ALGO_VANILLA)
             rc = fps_b200_vanilla_batch(src, B, P, C, n_samples, sp, dst, dp, (int)devs.size());
+        else if (algo == FPS_ALGO_KDTREE)
+            rc = fps_b200_kdtree_batch(src, B, P, C, n_samples, sp, dst, dp, (int)devs.size());
         else
             rc = fps_b200_kdline_batch(src, B, P, C, n_samples, sp, height, dst, dp, (int)devs.size());
     }
-    if (rc != 0) raise_rc(algo == FPS_ALGO_VANILLA ? "fps_b200_vanilla_batch" : "fps_b200_kdline_batch", rc);
+    if (rc != 0)
+        raise_rc(algo == FPS_ALGO_VANILLA ? "fps_b200_vanilla_batch" : algo == FPS_ALGO_KDTREE ? "fps_b200_kdtree_batch" : "fps_b200_kdline_batch", rc);
     return out;
 }
 
@@ -144,6 +175,11 @@ PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
           "Vanilla FPS. points: N x C float32; n_samples; start_idx: int or 1D uint64 array. Returns uint64[n_samples].");
     m.def("_bucket_fps_kdline_sampling", &kdline_py,
           "QuickFPS kd-line. points: N x C float32 (C <= 8); n_samples; height; start_idx: int. Returns uint64[n_samples].");
+    m.def("_bucket_fps_kdtree_sampling", &kdtree_py,
+          "QuickFPS full kd tree. points: N x C float32 (C <= 8); n_samples; start_idx: int. Returns uint64[n_samples].");
+    m.def("_bucket_fps_kdtree_sampling_batch",
+          [](farray p, size_t k, py::object s, py::object d) { return batch_py(FPS_ALGO_KDTREE, p, k, 0, s, d); },
+          "Batched QuickFPS full kd tree. points: B x N x C; start_idx: None|int|int[B]; devices: None|list[int].");
     m.def("_fps_sampling_batch",
           [](farray p, size_t k, py::object s, py::object d) { return batch_py(FPS_ALGO_VANILLA, p, k, 0, s, d); },
           "Batched vanilla FPS. points: B x N x C; start_idx: None|int|int[B]; devices: None|list[int].");

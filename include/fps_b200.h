@@ -58,6 +58,13 @@ FPS_API int fps_b200_vanilla(const float *points, size_t n, size_t dim, size_t k
 FPS_API int bucket_fps_kdline(const float *raw_data, size_t n_points, size_t dim, size_t n_samples,
                       size_t start_idx, size_t height, size_t *sampled_point_indices);
 
+/* QuickFPS full kd tree.  SAME NAME AND SIGNATURE as the reference's C ABI (src/wrapper.hpp:102-116 ->
+ * kdtree_sample :29-43 -> src/_ext/KDTree.h:13-52).  start_idx addresses the POSITION in the array after the
+ * (full-depth) kd build permuted it (src/wrapper.hpp:36-37); ties go to the HIGHEST position (the right child
+ * wins, src/_ext/KDNode.h:41-46).  Returns 1 for dim outside [1, 8], 2 for start_idx >= n_points. */
+FPS_API int bucket_fps_kdtree(const float *raw_data, size_t n_points, size_t dim, size_t n_samples,
+                      size_t start_idx, size_t *sampled_point_indices);
+
 /* ---- batches, host pointers (new; the reference has no batched entry) --------------------------- */
 
 /* B independent clouds [B][n][dim] -> [B][k].  start: NULL (all 0) or [B].  devices: NULL/0 = all
@@ -68,10 +75,14 @@ FPS_API int fps_b200_kdline_batch(const float *points, size_t B, size_t n, size_
                           const size_t *start, size_t height, size_t *out_indices, const int *devices,
                           int n_devices);
 
+FPS_API int fps_b200_kdtree_batch(const float *points, size_t B, size_t n, size_t dim, size_t k,
+                          const size_t *start, size_t *out_indices, const int *devices, int n_devices);
+
 /* ---- batches, device pointers (inputs already resident in HBM) ---------------------------------- */
 
 #define FPS_ALGO_VANILLA 0
 #define FPS_ALGO_KDLINE 1
+#define FPS_ALGO_KDTREE 2
 
 /* bytes of scratch the *_dev calls need on the current device for this shape (256-byte aligned base) */
 FPS_API size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t k, size_t height);
@@ -84,6 +95,9 @@ FPS_API int fps_b200_vanilla_batch_dev(const float *d_points, size_t B, size_t n
 FPS_API int fps_b200_kdline_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k,
                               const uint64_t *d_start, size_t height, uint64_t *d_out,
                               void *d_workspace, size_t workspace_bytes, void *stream);
+FPS_API int fps_b200_kdtree_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k,
+                              const uint64_t *d_start, uint64_t *d_out, void *d_workspace,
+                              size_t workspace_bytes, void *stream);
 
 /* kd-line build only (testing / inspection): d_perm [B][n] uint32 (position -> original id),
  * d_leaf_lo [B][2^h + 1] uint32 (slot s covers positions [lo[s], lo[s+1]); empty slots allowed),

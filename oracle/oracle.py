@@ -108,6 +108,18 @@ def kdline_eager(pc, k, h, start=0):
     return out
 
 
+def kdtree(pc, k, start=0):
+    """Oracle twin of fpsample.bucket_fps_kdtree_sampling (src/_ext/KDTree.h:13-52, src/wrapper.hpp:29-43): the build
+    permutes the array down to single points (KDTree.h:27, same split rules as the kd-line, KDTreeBase.h:84-207),
+    sampling starts at POSITION start, the right child wins distance ties (KDNode.h:41-46) = highest position: exact
+    FPS over the fully permuted rows with vanilla's tie rule.  Pinned against the compiled reference's outputs
+    (tests/golden: *_kdtree cases) and, where oracle/_ref exists, live (tests/test_oracle.py)."""
+    pc = _f32(pc)
+    perm, _, _ = kdline_build(pc, 1 << 20)   # depth limit far beyond any tree: leaves are single points
+    q = np.ascontiguousarray(pc[perm.astype(np.int64)])
+    return perm[fps_vanilla(q, k, start).astype(np.int64)].astype(np.uint64)
+
+
 def certify_vanilla(pc, picks, n_forced=1, n_threads=None):
     """True iff `picks` is exactly what fps_sampling yields from picks[:n_forced] (all host cores)."""
     pc = _f32(pc)

@@ -3,7 +3,7 @@ tests (oracle vs golden on CPU, CUDA path vs golden on the GPU).  Inputs are reg
 (fpsample_b200.synth); only the reference's OUTPUT indices are stored (tests/golden/golden.npz), plus a
 sha256 of every input so a drifting generator is detected instead of silently "passing".
 
-case = (id, input spec, call, params);   input spec = (generator, *args);   call in {"vanilla","kdline"}
+case = (id, input spec, call, params);   input spec = (generator, *args);   call in {"vanilla","kdline","kdtree"}
 """
 from __future__ import annotations
 
@@ -84,6 +84,18 @@ CASES = [
     ("n_odd_kd_h5", ("uniform", 60, 4099, 3), "kdline", dict(k=1000, h=5, start=4098)),
     ("k1_vanilla", ("uniform", 61, 100, 3), "vanilla", dict(k=1, start=42)),
     ("k1_kd", ("uniform", 61, 100, 3), "kdline", dict(k=1, h=3, start=42)),
+    # --- bucket_fps_kdtree_sampling (full kd tree) ----------------------------------
+    ("G0_kdtree", ("rand42", 4096, 3), "kdtree", dict(k=1024, start=0)),
+    ("G1_kdtree", ("uniform", 1, 4096, 3), "kdtree", dict(k=1024, start=0)),
+    ("G2_kdtree", ("uniform", 2, 16384, 3), "kdtree", dict(k=4096, start=5)),
+    ("G3_kdtree", ("uniform", 3, 100000, 3), "kdtree", dict(k=2048, start=0)),
+    ("dup_kdtree", ("dup", 10, 3), "kdtree", dict(k=5, start=2)),
+    *[(f"grid_d{d}_kdtree", ("grid", 10 + d, 3000, d), "kdtree", dict(k=500, start=d)) for d in (1, 2, 3, 6)],
+    ("grid_kdtree_all", ("grid", 98, 200, 3, 4), "kdtree", dict(k=200, start=7)),      # k == n, repeats legal
+    ("lidar_small_kdtree", ("lidar", 21, 20000), "kdtree", dict(k=2048, start=3)),
+    *[(f"dim{d}_kdtree", ("uniform", 40 + d, 2000, d), "kdtree", dict(k=300, start=d)) for d in (1, 2, 4, 5, 7, 8)],
+    ("n_odd_kdtree", ("uniform", 60, 4099, 3), "kdtree", dict(k=1000, start=4098)),
+    ("k1_kdtree", ("uniform", 61, 100, 3), "kdtree", dict(k=1, start=42)),
 ]
 
 CASE_BY_ID = {c[0]: c for c in CASES}

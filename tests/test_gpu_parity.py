@@ -31,6 +31,8 @@ def _need_gpu():
 def gpu_call(pc, call, p):
     if call == "vanilla":
         return capi.vanilla(pc, p["k"], p["start"])
+    if call == "kdtree":
+        return capi.kdtree(pc, p["k"], p["start"])
     return capi.kdline(pc, p["k"], p["h"], p["start"])
 
 
@@ -189,6 +191,33 @@ def test_grid_sampler(n, d, k, h, s, gen, oracle):
                 np.testing.assert_array_equal(gb[b], oracle.kdline(pcs[b], min(k, 500), h, [s, 0, 1][b]))
     finally:
         os.environ.pop("FPS_B200_GRID", None)
+
+
+@pytest.mark.parametrize("n,d,k,s,gen", [(4096, 3, 1024, 0, "u"), (50000, 3, 3000, 17, "l"), (3000, 2, 3000, 5, "g"), (7777, 6, 900, 3, "u"),
+                                         (20000, 1, 500, 0, "g"), (130000, 3, 1500, 9, "u"), (999, 8, 999, 998, "u")])
+def test_kdtree_vs_oracle(n, d, k, s, gen, oracle):
+    """bucket_fps_kdtree_sampling: the full kd permutation is built on the GPU (kdtree_build_kernel), the vanilla
+    kernels sample the permuted rows, positions are mapped back to ids."""
+    pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=11),
+          "l": lambda: synth.lidar(n, n)}[gen]()
+    got = capi.kdtree(pc, k, s)
+    assert "kdtree_build_kernel" in capi.last_plan(), capi.last_plan()
+    np.testing.assert_array_equal(got, oracle.kdtree(pc, k, s), err_msg=capi.last_plan())
+
+
+def test_kdtree_batch_and_python_api(oracle):
+    pcs = synth.uniform_batch(4400, 9, 3000, 3)
+    st = (np.arange(9) * 131) % 3000
+    got = fps.bucket_fps_kdtree_sampling_batch(pcs, 400, st, devices=[0])
+    assert got.dtype == np.uint64 and got.shape == (9, 400)
+    for b in range(9):
+        np.testing.assert_array_equal(got[b], oracle.kdtree(pcs[b], 400, int(st[b])))
+    one = fps.bucket_fps_kdtree_sampling(pcs[3].astype(np.float64), 400, start_idx=int(st[3]))
+    np.testing.assert_array_equal(one, got[3])
+    with pytest.raises(RuntimeError):   # the reference's dimension limit (src/wrapper.hpp:105-107)
+        fps.bucket_fps_kdtree_sampling(synth.uniform(1, 100, 9), 10, start_idx=0)
+    with pytest.raises(NotImplementedError):   # src/lib.cpp:482-485
+        fps._bucket_fps_kdtree_sampling(pcs[0], 10, np.array([1, 2], dtype=np.uint64))
 
 
 def test_unaligned_and_strided_inputs(oracle):

@@ -22,6 +22,8 @@ from fpsample_b200 import synth  # noqa: E402
 def run_oracle(O, pc, call, p):
     if call == "vanilla":
         return O.fps_vanilla(pc, p["k"], p["start"])
+    if call == "kdtree":
+        return O.kdtree(pc, p["k"], p["start"])
     return O.kdline(pc, p["k"], p["h"], p["start"])
 
 
@@ -70,6 +72,20 @@ def test_oracle_matches_compiled_reference_random(seed, oracle, ref):
     np.testing.assert_array_equal(oracle.kdline(pc, k, h, s), ref.bucket_fps_kdline_sampling(pc, k, h, s))
     starts = [int(x) for x in g.integers(0, n, size=min(4, k))]
     np.testing.assert_array_equal(oracle.fps_vanilla(pc, k, starts), ref.fps_sampling(pc, k, starts))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_kdtree_is_vanilla_over_the_full_permutation(seed, oracle, ref):
+    """bucket_fps_kdtree_sampling (src/_ext/KDTree.h:13-52) == exact FPS over the rows the full-depth kd build
+    permuted, from POSITION start, ties to the highest position (the right child wins, KDNode.h:41-46)."""
+    g = np.random.default_rng(300 + seed)
+    n = int(g.integers(64, 5000))
+    d = int(g.integers(1, 9))
+    k = int(g.integers(1, n))
+    s = int(g.integers(0, n))
+    pc = (synth.uniform(seed, n, d), synth.grid_ties(seed, n, d, levels=4), synth.lidar(seed, n))[seed % 3] if d == 3 or seed % 3 < 2 \
+        else synth.uniform(seed, n, d)
+    np.testing.assert_array_equal(oracle.kdtree(pc, k, s), ref.bucket_fps_kdtree_sampling(pc, k, s))
 
 
 def test_reference_error_codes(oracle):
