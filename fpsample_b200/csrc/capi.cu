@@ -258,7 +258,14 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
     bool force_grid = false;   // tests force the whole-GPU sampler onto clouds the planner would keep on one SM
     if (const char *e = getenv("FPS_B200_GRID")) force_grid = atoi(e) == 1;
-    L->warp = !build_only && !force_grid && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
+    if (const char *e = getenv("FPS_B200_GROUP")) force_grid = force_grid || atoi(e) == 1;
+    // medium clouds (>= 8192 points): groups of CTAs with batched picks beat one warp per cloud (1-3 clouds per SM)
+    bool prefer_group = false;
+    if (!build_only && !force_grid && n >= 8192) {
+        GridPlan tmp;
+        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp) && tmp.flat;
+    }
+    L->warp = !build_only && !force_grid && !prefer_group && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {
         L->async = false;
         L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
@@ -270,7 +277,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
     // (kdline_async.cu) covers what is left (2^h > 512 buckets)
     // one huge cloud: the whole GPU samples it, points in shared memory, batched picks (kdline_grid.cu)
-    L->grid = !build_only && (force_grid || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp);
+    L->grid = !build_only && (force_grid || prefer_group || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp);
     L->dist = !build_only && !L->grid && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
     L->async = !build_only && !L->grid && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
     if (L->async || L->dist || L->grid) {
@@ -283,7 +290,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         L->total = L->aux_off + (L->gridbuild ? B * kd_gridbuild_aux_bytes(n, dim, h) : 0);
         if (L->grid) {
             L->pub_off = (L->total + 255) & ~(size_t)255;
-            L->total = L->pub_off + kd_grid_pub_bytes(dim);
+            L->total = L->pub_off + kd_grid_pub_bytes(L->gp);
         }
     }
     return cudaSuccess;
@@ -332,10 +339,10 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
         tl_phase.mark(0, st);
-        set_plan("%s + kdline_grid_kernel<DIM=%d> clouds=%zu grid=%u threads=1024 points/thread=%u candidates/round<=%u smem=%zu "
-                 "region/cloud=%zu",
-                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.gp.dimp, B,
-                 L.gp.G, L.gp.ppt, L.gp.ecap, L.gp.smem, L.region_stride);
+        set_plan("%s + kdline_grid_kernel<DIM=%d,%s> clouds=%zu grid=%u (%u CTAs per cloud, %u clouds in flight) threads=1024 "
+                 "points/thread=%u candidates/round<=%u smem=%zu region/cloud=%zu",
+                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.gp.dimp,
+                 L.gp.flat ? "flat" : "merged", B, L.gp.G, L.gp.gc, L.gp.groups, L.gp.ppt, L.gp.ecap, L.gp.smem, L.region_stride);
         if (L.gridbuild)
             CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
                                    (u32)n, (u32)dim, (u32)h, st));

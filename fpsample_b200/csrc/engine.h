@@ -113,10 +113,10 @@ cudaError_t launch_kdline_dist(const DistPlan &pl, unsigned char *region, size_t
 // ---- kd-line, one huge cloud on the whole GPU: points in shared memory, batched picks per grid-wide exchange (kdline_grid.cu) --
 struct GridPlan {
     int dimp;
-    u32 ppt, G, ecap;
+    u32 ppt, G /* CTAs launched */, ecap, gc /* CTAs per cloud */, groups /* clouds in flight */, flat;
     size_t smem;
 };
-size_t kd_grid_pub_bytes(size_t dim);
+size_t kd_grid_pub_bytes(const GridPlan &pl);
 bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl);
 cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);

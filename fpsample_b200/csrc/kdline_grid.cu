@@ -63,7 +63,7 @@ struct GridArgs {
     const u64 *starts;
     u64 *out;
     uint4 *pub;          // [2][G][G_NK / 2] stamped 16-byte chunks (two 8-byte words each), zeroed before the launch
-    u32 B, n, npad, dim, k, ppt, ecap, S;
+    u32 B, n, npad, dim, k, ppt, ecap, S, gc;
 };
 
 // gpu-scope relaxed accesses: served by L2, never by a stale L1 line
@@ -96,11 +96,14 @@ __device__ __forceinline__ void bar_sync_named(u32 id, u32 nthreads) {
 __device__ __forceinline__ float f4get(const float4 &v, int e) { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; }
 __device__ __forceinline__ u64 key_max(u64 a, u64 b) { return a > b ? a : b; }
 
-template <int DIM>
+// FLAT = false: one huge cloud on the whole grid, every CTA merges its warps' keys and publishes its 8 largest.
+// FLAT = true : a batch of medium clouds, GROUPS of gc <= 8 CTAs per cloud; every warp publishes its own 3 largest keys
+//               + a bound (no CTA-level merge: with few CTAs per cloud the candidates per round would be too few).
+template <int DIM, bool FLAT>
 __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = warp_id();
-    const u32 G = gridDim.x, cta = blockIdx.x;
+    const u32 G = a.gc, cta = blockIdx.x % a.gc, grp = blockIdx.x / a.gc, ngrp = gridDim.x / a.gc;   // CTAs per cloud, my rank, my group
     const u32 npad = a.npad, dim = a.dim, k = a.k, S = a.S;
     const u32 NU = a.ppt >> 2;              // float4 per lane per component
     const u32 SL = 32u * a.ppt;             // positions per slice (one warp)
@@ -110,9 +113,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     // ---- shared memory carve ----------------------------------------------------------------------------------
     float4 *pts = reinterpret_cast<float4 *>(smem_raw);                         // [DIM + 1][PCQ]
     u64 *gk = reinterpret_cast<u64 *>(pts + (size_t)(DIM + 1) * PCQ);           // [G][G_NK] gathered keys
-    u64 *wtop = gk + (size_t)G_MAXG * G_NK;                                     // [G_W][4]: 2 keys, bound, pad
-    u64 *ekey = wtop + G_W * 4;                                                 // [G_ECAP]
-    u64 *red = ekey + G_ECAP;                                               // [8][4]
+    u64 *wtop = gk + (FLAT ? (size_t)8 * G_W * 4 : (size_t)G_MAXG * G_NK);                                     // [G_W][4]: 2 keys, bound, pad
+    u64 *ekey = wtop + G_W * 4;                                                 // [2][G_ECAP]
+    u64 *red = ekey + 2 * G_ECAP;                                               // [8][4]
     u32 *tpos = reinterpret_cast<u32 *>(red + 32);                              // [G_ECAP]
     float *tval = reinterpret_cast<float *>(tpos + G_ECAP);                     // [G_ECAP]
     float *tc = tval + G_ECAP;                                                  // [DIM][G_ECAP]
@@ -124,7 +127,8 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     u32 *pickw = lw + 16;                                                       // [8] pick mask words, [8] their exclusive prefix counts
     u32 *rowany = pickw + 16;                                                      // [G_ECAP]
     u32 *conf = rowany + G_ECAP;                                                // [G_ECAP][8] conflict bits
-    u32 *cum = conf + G_ECAP * 8;                                               // [S + 1] first slice of every leaf
+    u32 *slt = conf + G_ECAP * 8;                                               // [2][256] flat mode: first position / size of every slice
+    u32 *cum = slt + 512;                                               // [S + 1] first slice of every leaf
     enum { M_NREL = 0, M_STOP = 1, M_J = 2, M_E0 = 4 };
 
     float4 *pv = pts + (size_t)DIM * PCQ;   // running distances; padding slots hold -1 (never a candidate)
@@ -132,18 +136,60 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     u32 round = 0;                          // runs across clouds
 #if GDBG
     u64 dbg[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const bool dbg_on = (tid == 0 && cta == 0);
+    const bool dbg_on = (tid == 0 && blockIdx.x == 0);
 #endif
 
-    for (u32 cloud = 0; cloud < a.B; ++cloud) {
+    constexpr u32 WK = FLAT ? 4u : 0u;                                   // flat: words a warp publishes (3 keys + bound)
+    uint4 *pubg = a.pub + (size_t)grp * 2 * (FLAT ? G * G_W * 2 : G * (G_NK / 2));   // this group's two exchange buffers
+    for (u32 cloud = grp; cloud < a.B; cloud += ngrp) {
         unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
         const float *q = reinterpret_cast<const float *>(rg);
         const u32 *perm = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 1) * npad;
         const u32 *nlo = perm + npad;
         u64 *out = a.out + (size_t)cloud * k;
 
-        // ---- leaf b owns the slices [cum[b], cum[b+1]), ceil(size / SL) of them.  Warp 0 scans the leaf sizes. ----------
         if (tid < 2 * DIM) cbox[tid] = tid < DIM ? 0x7fffffff : (int)0x80000000;
+        u32 wpos0 = 0, wcnt = 0;   // this warp's slice: positions [wpos0, wpos0 + wcnt) of the permuted array
+        if constexpr (FLAT) {
+            // ---- a slice = the largest kd SUBTREE (aligned block of 2^j leaves) that fits SL positions: spatially as
+            //      compact as the tree makes it; a leaf beyond SL positions is cut into several slices.  If the cloud needs
+            //      more slices than the group has warps, fall back to plain position ranges (any slicing is exact, the
+            //      boxes are just looser).
+            for (u32 b = tid; b <= S; b += G_T) cum[b] = __ldg(nlo + b);
+            __syncthreads();
+            if (tid == 0) {
+                const u32 cap = G * G_W;
+                u32 ns = 0, pos = 0;
+                bool ok = true;
+                while (pos < S && ok) {
+                    u32 j = pos ? (u32)__ffs(pos) - 1u : 31u;
+                    while ((1u << j) > S - pos) --j;
+                    while (j > 0 && cum[pos + (1u << j)] - cum[pos] > SL) --j;
+                    const u32 lo = cum[pos], cnt = cum[pos + (1u << j)] - lo;
+                    const u32 need = (cnt + SL - 1) / SL;
+                    if (ns + need > cap) ok = false;
+                    else
+                        for (u32 x = 0; x < need; ++x) {
+                            slt[ns] = lo + x * SL;
+                            slt[256 + ns] = min(SL, cnt - x * SL);
+                            ++ns;
+                        }
+                    pos += 1u << j;
+                }
+                if (!ok) {
+                    ns = 0;
+                    for (u32 p0 = 0; p0 < a.n; p0 += SL, ++ns) {
+                        slt[ns] = p0;
+                        slt[256 + ns] = min(SL, a.n - p0);
+                    }
+                }
+                for (; ns < cap; ++ns) slt[ns] = slt[256 + ns] = 0;
+            }
+            __syncthreads();
+            wpos0 = slt[cta * G_W + warp];
+            wcnt = slt[256 + cta * G_W + warp];
+        } else {
+        // ---- leaf b owns the slices [cum[b], cum[b+1]), ceil(size / SL) of them.  Warp 0 scans the leaf sizes. ----------
         if (warp == 0) {
             u32 carry = 0;
             for (u32 b0 = 0; b0 < S; b0 += 32) {
@@ -161,8 +207,6 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             if (lane == 0) cum[S] = carry;
         }
         __syncthreads();
-        // this warp's slice: positions [wpos0, wpos0 + wcnt) of the permuted array
-        u32 wpos0 = 0, wcnt = 0;
         {
             const u32 g = cta * G_W + warp;
             if (g < cum[S]) {
@@ -176,6 +220,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 wpos0 = l0 + (g - cum[lo]) * SL;
                 wcnt = min(SL, l1 - wpos0);
             }
+        }
         }
         float wlo[DIM], whi[DIM];
         {
@@ -244,18 +289,26 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             u64 k1 = v1 < 0.0f ? 0ull : make_key(v1, G_LOW - p1), k2 = v2 < 0.0f ? 0ull : make_key(v2, G_LOW - p2),
                 k3 = v3 < 0.0f ? 0ull : make_key(v3, G_LOW - p3);
-            u64 res[3];
+            u64 res[4] = {0ull, 0ull, 0ull, 0ull};
+            u32 pops = 0;
 #pragma unroll
             for (int e = 0; e < 3; ++e) {
                 const u64 wk = warp_max_key(k1);
                 res[e] = wk;
-                if (e < 2 && wk != 0ull && k1 == wk) {
+                if ((FLAT || e < 2) && wk != 0ull && k1 == wk) {
                     k1 = k2;
                     k2 = k3;
                     k3 = 0ull;
+                    ++pops;
                 }
             }
-            if (lane < 3) wtop[warp * 4 + lane] = lane == 0 ? res[0] : lane == 1 ? res[1] : res[2];
+            if constexpr (FLAT) {   // three candidates + the fourth key as the slice bound
+                res[3] = warp_max_key(k1);
+                // a lane popped three times no longer knows its next key: everything it holds sorts below its third,
+                // so the third key itself is a valid (conservative) bound
+                if (__any_sync(FULL, pops >= 3)) res[3] = res[2];
+            }
+            if (lane < 4) wtop[warp * 4 + lane] = lane == 0 ? res[0] : lane == 1 ? res[1] : lane == 2 ? res[2] : res[3];
             smax = __uint_as_float((u32)(res[0] >> 32));
         };
 
@@ -342,10 +395,17 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             const u32 stamp = (round + 1) & ((1u << (32 - G_PBITS)) - 1u);
             const u32 sbits = stamp << G_PBITS;
             float ctamax;
-            {
+            if constexpr (FLAT) {   // every warp publishes its own four words: no CTA-level merge, no barrier
+                ctamax = 0.0f;      // derived from the gathered keys below
+                u64 *dst = reinterpret_cast<u64 *>(pubg) + (((size_t)(round & 1u) * G + cta) * G_W + warp) * WK;
+                if (lane < WK) {
+                    const u64 w = wtop[warp * 4 + lane];
+                    stg_relaxed_v2(dst + lane, (u32)(w >> 32), (w ? G_LOW - (u32)w : G_PNONE) | sbits);
+                }
+            } else {
                 const u64 a0 = wtop[lane * 4], a1 = wtop[lane * 4 + 1];
                 ctamax = __uint_as_float(__reduce_max_sync(FULL, (u32)(a0 >> 32)));
-                u64 *dst = reinterpret_cast<u64 *>(a.pub) + ((size_t)(round & 1u) * G + cta) * G_NK;
+                u64 *dst = reinterpret_cast<u64 *>(pubg) + ((size_t)(round & 1u) * G + cta) * G_NK;
 #pragma unroll 1
                 for (u32 s2 = 0; s2 < 2; ++s2) {
                     const u64 mk = wtop[warp * 4 + s2];
@@ -364,8 +424,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             const long long c2 = GCLK();
             // ================= C: gather every CTA's words (the grid-wide synchronisation): one 16-byte chunk per thread ====
-            if (tid < G * (G_NK / 2)) {
-                const uint4 *src = a.pub + (size_t)(round & 1u) * G * (G_NK / 2) + tid;
+            const u32 NCHK = FLAT ? G * G_W * (WK / 2) : G * (G_NK / 2);   // 16-byte chunks of one exchange buffer
+            if (tid < NCHK) {
+                const uint4 *src = pubg + (size_t)(round & 1u) * NCHK + tid;
                 uint4 v;
                 do {
                     v = ldg_relaxed_v4(src);
@@ -376,6 +437,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             __syncwarp();   // lanes leave the spin loop one by one: converge before the warp collectives below
             if (tid < 16) wflag[tid] = 0;
+            if (tid < 2) misc[M_E0 + tid] = 0;
             if (tid == 0) {
                 misc[M_NREL] = 0;
             }
@@ -387,7 +449,39 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             // most ECAP candidates (three lists are built at once).
             const u32 NWG = (G + 31) >> 5;   // warps holding CTAs: thread c < G looks after CTA c's ten keys
             long long d1 = c3;
-            if (warp < NWG) {
+            if constexpr (FLAT) {
+                // every warp of the group published {k0, k1, k2, bound}.  Candidates: the three keys of every warp against
+                // Bd3 = the largest bound; if that leaves more than ECAP, only the first key of every warp against Bd1 =
+                // the largest second key (at most 256 warps).  Every warp derives the two thresholds itself: no barrier.
+                const u32 NWP = G * G_W;
+                u64 b3 = 0ull, b1 = 0ull;
+                u32 cm = 0;
+                for (u32 w = lane; w < NWP; w += 32) {
+                    b3 = key_max(b3, gk[w * 4 + 3]);
+                    b1 = key_max(b1, gk[w * 4 + 1]);
+                    if (w / G_W == cta) cm = max(cm, (u32)(gk[w * 4] >> 32));
+                }
+                const u64 Bd3 = warp_max_key(b3), Bd1 = warp_max_key(b1);
+                ctamax = __uint_as_float(__reduce_max_sync(FULL, cm));
+#pragma unroll 1
+                for (u32 idx0 = 0; idx0 < NWP * 3; idx0 += G_T) {
+                    if (idx0 + warp * 32 >= NWP * 3) break;   // warp-uniform
+                    const u32 idx = idx0 + tid, w = idx / 3, e = idx - w * 3;
+                    const u64 kk = idx < NWP * 3 ? gk[w * 4 + e] : 0ull;
+                    const bool f3 = kk > Bd3, f1 = e == 0 && kk > Bd1;
+                    const u32 m3 = __ballot_sync(FULL, f3), m1 = __ballot_sync(FULL, f1);
+                    u32 o3 = 0, o1 = 0;
+                    if (lane == 0) {
+                        if (m3) o3 = atomicAdd(&misc[M_E0], (u32)__popc(m3));
+                        if (m1) o1 = atomicAdd(&misc[M_E0 + 1], (u32)__popc(m1));
+                    }
+                    const u32 lt = (1u << lane) - 1u;
+                    o3 = __shfl_sync(FULL, o3, 0) + __popc(m3 & lt);
+                    o1 = __shfl_sync(FULL, o1, 0) + __popc(m1 & lt);
+                    if (f3 && o3 < G_ECAP) ekey[o3] = kk;
+                    if (f1 && o1 < G_ECAP) ekey[G_ECAP + o1] = kk;
+                }
+            } else if (warp < NWG) {
                 u64 kc[G_NK];
 #pragma unroll
                 for (u32 e = 0; e < G_NK; ++e) kc[e] = tid < G ? gk[tid * G_NK + e] : 0ull;
@@ -444,8 +538,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             __syncthreads();
             const long long d2 = GCLK();
-            const u32 E = min(misc[M_E0], G_ECAP);
-            const u64 *ek = ekey;
+            const u32 vflat = (FLAT && misc[M_E0] > ECAP) ? 1u : 0u;
+            const u32 E = min(misc[M_E0 + vflat], G_ECAP);
+            const u64 *ek = ekey + vflat * G_ECAP;
             // rank by counting: 1024 / E2 adjacent lanes per candidate (E2 = E rounded up to a power of two >= 32); the
             // candidate's coordinates are fetched from the region (L2) meanwhile
             {
@@ -620,7 +715,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             ++round;
             __syncthreads();
 #if GDBG
-            if (tid == 0 && round - 1 < 4096) g_grid_trace[(round - 1) * 160 + cta] = (u32)(c1 - c0);
+            if (tid == 0 && round - 1 < 4096) g_grid_trace[(round - 1) * 160 + (blockIdx.x % 160)] = (u32)(c1 - c0);
             if (dbg_on) {
                 const long long c6 = GCLK();
                 dbg[0] += 1;
@@ -663,55 +758,89 @@ __global__ void grid_map_kernel(u64 *out, const unsigned char *region, size_t re
 // ======================================================================================================
 static int pad_dim_g(int dim) { return dim <= 2 ? 2 : dim == 3 ? 3 : dim == 4 ? 4 : dim <= 6 ? 6 : 8; }
 
-static size_t grid_smem(int dimp, u32 ppt, size_t S) {
+static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat) {
     const size_t pcq = (size_t)G_W * (ppt / 4) * 32;
     size_t b = (size_t)(dimp + 1) * pcq * 16;            // points
-    b += (size_t)G_MAXG * G_NK * 8;                      // gathered keys
-    b += G_W * 4 * 8 + G_ECAP * 8 + 32 * 8;              // wtop, ekey, red
+    b += flat ? (size_t)8 * G_W * 4 * 8 : (size_t)G_MAXG * G_NK * 8;   // gathered keys
+    b += G_W * 4 * 8 + 2 * G_ECAP * 8 + 32 * 8;          // wtop, ekey, red
     b += (size_t)G_ECAP * 4 * 2;                         // tpos, tval
     b += (size_t)dimp * G_ECAP * 4 + G_ECAP * 4;         // tc, rel
     b += 2 * dimp * 4 + 16 * 4 + 16 * 4 + (S + 1) * 4;   // cbox, misc, wflag, cum
-    b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4;           // lw, pickw, rowany, conf
+    b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4 + 512 * 4; // lw, pickw, rowany, conf, slt
     return (b + 15) & ~(size_t)15;
 }
 
-size_t kd_grid_pub_bytes(size_t) { return (size_t)2 * G_MAXG * G_NK * 8; }
+size_t kd_grid_pub_bytes(const GridPlan &pl) {
+    return pl.flat ? (size_t)pl.groups * 2 * pl.gc * G_W * 4 * 8 : (size_t)2 * G_MAXG * G_NK * 8;
+}
 
 bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl) {
     if (dim == 0 || dim > 8 || h == 0 || n == 0 || B == 0 || n >= G_PNONE) return false;
     int want = -1;
     if (const char *e = getenv("FPS_B200_GRID")) want = atoi(e);
     if (want == 0) return false;
-    if (want < 0 && (n < 262144 || B > 4)) return false;   // one huge cloud at a time; batches go to the other samplers
     const int dimp = pad_dim_g((int)dim);
     const size_t sms = n_sms < (int)G_MAXG ? n_sms : G_MAXG;
     const size_t S = (size_t)1 << (h < 20 ? h : 20);
-    // slices never straddle a leaf: at most ceil(n / SL) + S of them (every leaf ends with one partial slice)
-    u32 ppt = 0, G = 0;
-    for (u32 p = 4; p <= 16 && !ppt; p += 4) {
-        const size_t SL = 32 * (size_t)p, slices = (n + SL - 1) / SL + S;
-        const size_t g = (slices + G_W - 1) / G_W;
-        if (g <= sms && grid_smem(dimp, p, S) <= 227 * 1024) {
-            ppt = p;
-            G = (u32)g;
-        }
-    }
-    if (!ppt) return false;
     pl->dimp = dimp;
-    pl->ppt = ppt;
-    pl->G = G;
-    pl->smem = grid_smem(dimp, ppt, S);
     pl->ecap = G_ECAP;
     if (const char *e = getenv("FPS_B200_GRID_ECAP")) {
         const int v = atoi(e);
         if (v >= 32 && v <= (int)G_ECAP) pl->ecap = (u32)v;
     }
+    // ---- a batch of medium clouds: groups of gc <= 8 CTAs per cloud, every warp publishes its own keys (flat mode) ------
+    int grp = -1;
+    if (const char *e = getenv("FPS_B200_GROUP")) grp = atoi(e);
+    const bool medium = n >= 8192 && n < 262144 && S <= 4096;
+    // measured (scripts/cmp_group.py): 1.4x - 3x faster than the cluster coordinator/worker kernel and than the one-warp-per-
+    // cloud kernel on every shape from 8192 points up (FPS_B200_GROUP=0 switches it off)
+    const bool group_default = true;
+    if (grp != 0 && (grp == 1 || (want < 0 && medium && group_default)) && want != 1) {
+        for (u32 p = 12; p >= 4; p -= 4) {
+            if (grid_smem(dimp, p, S, true) > 227 * 1024) continue;
+            const size_t per_cta = (size_t)G_T * p;
+            for (u32 gc = 1; gc <= 8; gc *= 2) {
+                // room for the subtree packing: ~20 % slack (a tighter fit falls back to position ranges in the kernel)
+                if (gc * per_cta * 5 < n * 6) continue;
+                if (gc > sms) break;
+                size_t groups = sms / gc;
+                if (groups > B) groups = B;
+                // worth it when the groups keep most of the GPU busy or the clouds are few
+                pl->ppt = p;
+                pl->gc = gc;
+                pl->groups = (u32)groups;
+                pl->G = (u32)(groups * gc);
+                pl->flat = 1;
+                pl->smem = grid_smem(dimp, p, S, true);
+                return true;
+            }
+        }
+        if (grp == 1) return false;
+    }
+    if (want < 0 && (n < 262144 || B > 4)) return false;   // one huge cloud at a time; batches go to the other samplers
+    // slices never straddle a leaf: at most ceil(n / SL) + S of them (every leaf ends with one partial slice)
+    u32 ppt = 0, G = 0;
+    for (u32 p = 4; p <= 16 && !ppt; p += 4) {
+        const size_t SL = 32 * (size_t)p, slices = (n + SL - 1) / SL + S;
+        const size_t g = (slices + G_W - 1) / G_W;
+        if (g <= sms && grid_smem(dimp, p, S, false) <= 227 * 1024) {
+            ppt = p;
+            G = (u32)g;
+        }
+    }
+    if (!ppt) return false;
+    pl->ppt = ppt;
+    pl->G = G;
+    pl->gc = G;
+    pl->groups = 1;
+    pl->flat = 0;
+    pl->smem = grid_smem(dimp, ppt, S, false);
     return true;
 }
 
-template <int DIM>
+template <int DIM, bool FLAT>
 static cudaError_t launch_grid_t(const GridPlan &pl, GridArgs &a, cudaStream_t st) {
-    auto kern = kdline_grid_kernel<DIM>;
+    auto kern = kdline_grid_kernel<DIM, FLAT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     void *params[] = {&a};
@@ -761,14 +890,25 @@ cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t
     a.k = k;
     a.ppt = pl.ppt;
     a.ecap = pl.ecap;
-    cudaError_t e = cudaMemsetAsync(pub, 0, kd_grid_pub_bytes(dim), st);
+    a.gc = pl.gc;
+    cudaError_t e = cudaMemsetAsync(pub, 0, kd_grid_pub_bytes(pl), st);
     if (e != cudaSuccess) return e;
-    switch (pl.dimp) {
-        case 2: e = launch_grid_t<2>(pl, a, st); break;
-        case 3: e = launch_grid_t<3>(pl, a, st); break;
-        case 4: e = launch_grid_t<4>(pl, a, st); break;
-        case 6: e = launch_grid_t<6>(pl, a, st); break;
-        default: e = launch_grid_t<8>(pl, a, st); break;
+    if (pl.flat) {
+        switch (pl.dimp) {
+            case 2: e = launch_grid_t<2, true>(pl, a, st); break;
+            case 3: e = launch_grid_t<3, true>(pl, a, st); break;
+            case 4: e = launch_grid_t<4, true>(pl, a, st); break;
+            case 6: e = launch_grid_t<6, true>(pl, a, st); break;
+            default: e = launch_grid_t<8, true>(pl, a, st); break;
+        }
+    } else {
+        switch (pl.dimp) {
+            case 2: e = launch_grid_t<2, false>(pl, a, st); break;
+            case 3: e = launch_grid_t<3, false>(pl, a, st); break;
+            case 4: e = launch_grid_t<4, false>(pl, a, st); break;
+            case 6: e = launch_grid_t<6, false>(pl, a, st); break;
+            default: e = launch_grid_t<8, false>(pl, a, st); break;
+        }
     }
     count_launch();
     if (e != cudaSuccess) return e;

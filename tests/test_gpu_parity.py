@@ -112,16 +112,22 @@ def test_tie_clouds(seed, oracle):
 
 @pytest.mark.parametrize("n,d,levels,k,h,s", [(60000, 3, 24, 3000, 6, 5), (40000, 2, 40, 2500, 8, 0), (30000, 6, 3, 1500, 7, 9),
                                               (70000, 1, 5000, 2000, 5, 1), (20000, 3, 2, 500, 10, 0)])
-def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle):
-    """clouds too big for one SM go through the coordinator/worker cluster kernel: ties, duplicates and
-    near-empty buckets must not disturb its upper-bound logic."""
+def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle, monkeypatch):
+    """clouds too big for one SM go through the coordinator/worker cluster kernel (the planner now prefers the grouped
+    grid sampler for them: switched off here): ties, duplicates and near-empty buckets must not disturb its
+    upper-bound logic."""
+    monkeypatch.setenv("FPS_B200_GROUP", "0")
     g = synth.grid_ties(n + h, n, d, levels=levels)
     got = capi.kdline(g, k, h, s)
     assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warpg_kernel")), capi.last_plan()
     np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
+    monkeypatch.delenv("FPS_B200_GROUP")
+    got = capi.kdline(g, k, h, s)   # and the default route
+    np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
 
 
-def test_async_batches_and_cluster_sizes(oracle):
+def test_async_batches_and_cluster_sizes(oracle, monkeypatch):
+    monkeypatch.setenv("FPS_B200_GROUP", "0")
     for B, n, k, h in [(3, 30000, 800, 7), (20, 20000, 400, 6), (80, 16384, 300, 7), (160, 14000, 200, 5)]:
         pcs = synth.uniform_batch(8000 + B, B, n, 3)
         st = (np.arange(B) * 7) % n
@@ -137,6 +143,7 @@ def test_alternative_samplers(env, oracle):
     """every kd-line sampler must give the reference's indices, not only the one the planner prefers: the
     one-warp-per-cloud kernel over global memory (big batches), the distributed-bucket cluster kernel (opt-in),
     the eager variant of the warp kernel and its shared-memory-only placement."""
+    env = dict(env, FPS_B200_GROUP="0")   # the planner's default for medium clouds is the grouped grid sampler: off here
     os.environ.update(env)
     try:
         want_plan = {"FPS_B200_WARP_GLOBAL_MINB": "kdline_warpg_kernel", "FPS_B200_DIST": "kdline_dist_kernel",
@@ -218,6 +225,26 @@ def test_kdtree_batch_and_python_api(oracle):
         fps.bucket_fps_kdtree_sampling(synth.uniform(1, 100, 9), 10, start_idx=0)
     with pytest.raises(NotImplementedError):   # src/lib.cpp:482-485
         fps._bucket_fps_kdtree_sampling(pcs[0], 10, np.array([1, 2], dtype=np.uint64))
+
+
+@pytest.mark.parametrize("n,d,k,h,s,gen,B", [(16384, 3, 4096, 7, 0, "u", 5), (30000, 3, 900, 7, 11, "u", 1), (20000, 6, 500, 6, 3, "u", 3),
+                                             (40000, 2, 800, 5, 1, "g", 2), (60000, 3, 2000, 9, 0, "l", 1), (9000, 1, 9000, 5, 2, "g", 2),
+                                             (12345, 4, 700, 8, 5, "u", 150), (25000, 8, 600, 7, 9, "u", 2)])
+def test_group_sampler(n, d, k, h, s, gen, B, oracle):
+    """batches of medium clouds on groups of CTAs (kdline_grid_kernel, flat mode: every warp publishes its own keys,
+    slices = kd subtrees): more clouds than groups, ties, duplicates, every padded dimension."""
+    os.environ["FPS_B200_GROUP"] = "1"
+    try:
+        mk = {"u": lambda i: synth.uniform(n + d + i, n, d), "g": lambda i: synth.grid_ties(n + i, n, d, levels=23),
+              "l": lambda i: synth.lidar(n + i, n)}[gen]
+        pcs = np.stack([mk(i) for i in range(B)])
+        st = (np.arange(B) * 37 + s) % n
+        got = capi.kdline_batch(pcs, k, h, st, devices=[0])
+        assert "kdline_grid_kernel" in capi.last_plan() and "flat" in capi.last_plan(), capi.last_plan()
+        for b in sorted({0, B // 2, B - 1}):
+            np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, int(st[b])), err_msg=f"cloud {b}: {capi.last_plan()}")
+    finally:
+        os.environ.pop("FPS_B200_GROUP", None)
 
 
 def test_unaligned_and_strided_inputs(oracle):
