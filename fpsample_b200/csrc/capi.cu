@@ -263,7 +263,9 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     bool prefer_group = false;
     if (!build_only && !force_grid && n >= 8192) {
         GridPlan tmp;
-        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp) && tmp.flat;
+        // ... unless the batch is big enough for the one-warp-per-cloud streaming kernel (>= 4 clouds per SM in flight,
+        // HBM-bound: BASELINE.json cfg 5) and a cloud would tie up 4 or more SMs
+        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp) && tmp.flat && (tmp.gc <= 2 || B < (size_t)4 * n_sms);
     }
     L->warp = !build_only && !force_grid && !prefer_group && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {

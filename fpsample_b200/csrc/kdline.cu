@@ -26,7 +26,9 @@
 
 namespace fps {
 __device__ unsigned long long g_kb_dbg[16];
+#ifndef KBDBG
 #define KBDBG 0   // 1: per-phase clock64 counters of cloud 0 (scripts/time_build.py prints them)
+#endif
 
 struct KdFixedSmem {
     u64 wslot[2][32];

@@ -97,7 +97,7 @@ __device__ __forceinline__ float f4get(const float4 &v, int e) { return e == 0 ?
 __device__ __forceinline__ u64 key_max(u64 a, u64 b) { return a > b ? a : b; }
 
 // FLAT = false: one huge cloud on the whole grid, every CTA merges its warps' keys and publishes its 8 largest.
-// FLAT = true : a batch of medium clouds, GROUPS of gc <= 8 CTAs per cloud; every warp publishes its own 3 largest keys
+// FLAT = true : a batch of medium clouds, GROUPS of gc <= 16 CTAs per cloud; every warp publishes its own 3 largest keys
 //               + a bound (no CTA-level merge: with few CTAs per cloud the candidates per round would be too few).
 template <int DIM, bool FLAT>
 __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     // ---- shared memory carve ----------------------------------------------------------------------------------
     float4 *pts = reinterpret_cast<float4 *>(smem_raw);                         // [DIM + 1][PCQ]
     u64 *gk = reinterpret_cast<u64 *>(pts + (size_t)(DIM + 1) * PCQ);           // [G][G_NK] gathered keys
-    u64 *wtop = gk + (FLAT ? (size_t)8 * G_W * 4 : (size_t)G_MAXG * G_NK);                                     // [G_W][4]: 2 keys, bound, pad
+    u64 *wtop = gk + (FLAT ? (size_t)G * G_W * 4 : (size_t)G_MAXG * G_NK);                                     // [G_W][4]: 2 keys, bound, pad
     u64 *ekey = wtop + G_W * 4;                                                 // [2][G_ECAP]
     u64 *red = ekey + 2 * G_ECAP;                                               // [8][4]
     u32 *tpos = reinterpret_cast<u32 *>(red + 32);                              // [G_ECAP]
@@ -127,8 +127,8 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     u32 *pickw = lw + 16;                                                       // [8] pick mask words, [8] their exclusive prefix counts
     u32 *rowany = pickw + 16;                                                      // [G_ECAP]
     u32 *conf = rowany + G_ECAP;                                                // [G_ECAP][8] conflict bits
-    u32 *slt = conf + G_ECAP * 8;                                               // [2][256] flat mode: first position / size of every slice
-    u32 *cum = slt + 512;                                               // [S + 1] first slice of every leaf
+    u32 *slt = conf + G_ECAP * 8;                                               // [2][512] flat mode: first position / size of every slice
+    u32 *cum = slt + 1024;                                               // [S + 1] first slice of every leaf
     enum { M_NREL = 0, M_STOP = 1, M_J = 2, M_E0 = 4 };
 
     float4 *pv = pts + (size_t)DIM * PCQ;   // running distances; padding slots hold -1 (never a candidate)
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     else
                         for (u32 x = 0; x < need; ++x) {
                             slt[ns] = lo + x * SL;
-                            slt[256 + ns] = min(SL, cnt - x * SL);
+                            slt[512 + ns] = min(SL, cnt - x * SL);
                             ++ns;
                         }
                     pos += 1u << j;
@@ -180,14 +180,14 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     ns = 0;
                     for (u32 p0 = 0; p0 < a.n; p0 += SL, ++ns) {
                         slt[ns] = p0;
-                        slt[256 + ns] = min(SL, a.n - p0);
+                        slt[512 + ns] = min(SL, a.n - p0);
                     }
                 }
-                for (; ns < cap; ++ns) slt[ns] = slt[256 + ns] = 0;
+                for (; ns < cap; ++ns) slt[ns] = slt[512 + ns] = 0;
             }
             __syncthreads();
             wpos0 = slt[cta * G_W + warp];
-            wcnt = slt[256 + cta * G_W + warp];
+            wcnt = slt[512 + cta * G_W + warp];
         } else {
         // ---- leaf b owns the slices [cum[b], cum[b+1]), ceil(size / SL) of them.  Warp 0 scans the leaf sizes. ----------
         if (warp == 0) {
@@ -452,16 +452,18 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             if constexpr (FLAT) {
                 // every warp of the group published {k0, k1, k2, bound}.  Candidates: the three keys of every warp against
                 // Bd3 = the largest bound; if that leaves more than ECAP, only the first key of every warp against Bd1 =
-                // the largest second key (at most 256 warps).  Every warp derives the two thresholds itself: no barrier.
+                // the largest second key; if even that is too many (up to 512 warps), the single largest key -- always a
+                // valid round.  Every warp derives the thresholds itself: no barrier.
                 const u32 NWP = G * G_W;
-                u64 b3 = 0ull, b1 = 0ull;
+                u64 b3 = 0ull, b1 = 0ull, b0 = 0ull;
                 u32 cm = 0;
                 for (u32 w = lane; w < NWP; w += 32) {
                     b3 = key_max(b3, gk[w * 4 + 3]);
                     b1 = key_max(b1, gk[w * 4 + 1]);
+                    b0 = key_max(b0, gk[w * 4]);
                     if (w / G_W == cta) cm = max(cm, (u32)(gk[w * 4] >> 32));
                 }
-                const u64 Bd3 = warp_max_key(b3), Bd1 = warp_max_key(b1);
+                const u64 Bd3 = warp_max_key(b3), Bd1 = warp_max_key(b1), Top = warp_max_key(b0);
                 ctamax = __uint_as_float(__reduce_max_sync(FULL, cm));
 #pragma unroll 1
                 for (u32 idx0 = 0; idx0 < NWP * 3; idx0 += G_T) {
@@ -481,6 +483,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     if (f3 && o3 < G_ECAP) ekey[o3] = kk;
                     if (f1 && o1 < G_ECAP) ekey[G_ECAP + o1] = kk;
                 }
+                if (tid == 0) red[28] = Top;
             } else if (warp < NWG) {
                 u64 kc[G_NK];
 #pragma unroll
@@ -538,9 +541,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             }
             __syncthreads();
             const long long d2 = GCLK();
-            const u32 vflat = (FLAT && misc[M_E0] > ECAP) ? 1u : 0u;
-            const u32 E = min(misc[M_E0 + vflat], G_ECAP);
-            const u64 *ek = ekey + vflat * G_ECAP;
+            const u32 vflat = (FLAT && misc[M_E0] > ECAP) ? (misc[M_E0 + 1] > ECAP ? 2u : 1u) : 0u;
+            const u32 E = vflat == 2 ? 1u : min(misc[M_E0 + vflat], G_ECAP);
+            const u64 *ek = vflat == 2 ? red + 28 : ekey + vflat * G_ECAP;
             // rank by counting: 1024 / E2 adjacent lanes per candidate (E2 = E rounded up to a power of two >= 32); the
             // candidate's coordinates are fetched from the region (L2) meanwhile
             {
@@ -758,15 +761,15 @@ __global__ void grid_map_kernel(u64 *out, const unsigned char *region, size_t re
 // ======================================================================================================
 static int pad_dim_g(int dim) { return dim <= 2 ? 2 : dim == 3 ? 3 : dim == 4 ? 4 : dim <= 6 ? 6 : 8; }
 
-static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat) {
+static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat, u32 gc = 16) {
     const size_t pcq = (size_t)G_W * (ppt / 4) * 32;
     size_t b = (size_t)(dimp + 1) * pcq * 16;            // points
-    b += flat ? (size_t)8 * G_W * 4 * 8 : (size_t)G_MAXG * G_NK * 8;   // gathered keys
+    b += flat ? (size_t)gc * G_W * 4 * 8 : (size_t)G_MAXG * G_NK * 8;  // gathered keys
     b += G_W * 4 * 8 + 2 * G_ECAP * 8 + 32 * 8;          // wtop, ekey, red
     b += (size_t)G_ECAP * 4 * 2;                         // tpos, tval
     b += (size_t)dimp * G_ECAP * 4 + G_ECAP * 4;         // tc, rel
     b += 2 * dimp * 4 + 16 * 4 + 16 * 4 + (S + 1) * 4;   // cbox, misc, wflag, cum
-    b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4 + 512 * 4; // lw, pickw, rowany, conf, slt
+    b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4 + 1024 * 4;// lw, pickw, rowany, conf, slt
     return (b + 15) & ~(size_t)15;
 }
 
@@ -797,9 +800,9 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
     const bool group_default = true;
     if (grp != 0 && (grp == 1 || (want < 0 && medium && group_default)) && want != 1) {
         for (u32 p = 12; p >= 4; p -= 4) {
-            if (grid_smem(dimp, p, S, true) > 227 * 1024) continue;
             const size_t per_cta = (size_t)G_T * p;
-            for (u32 gc = 1; gc <= 8; gc *= 2) {
+            for (u32 gc = 1; gc <= 16; gc *= 2) {
+                if (grid_smem(dimp, p, S, true, gc) > 227 * 1024) break;
                 // room for the subtree packing: ~20 % slack (a tighter fit falls back to position ranges in the kernel)
                 if (gc * per_cta * 5 < n * 6) continue;
                 if (gc > sms) break;
@@ -811,7 +814,7 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
                 pl->groups = (u32)groups;
                 pl->G = (u32)(groups * gc);
                 pl->flat = 1;
-                pl->smem = grid_smem(dimp, p, S, true);
+                pl->smem = grid_smem(dimp, p, S, true, gc);
                 return true;
             }
         }

@@ -229,7 +229,8 @@ def test_kdtree_batch_and_python_api(oracle):
 
 @pytest.mark.parametrize("n,d,k,h,s,gen,B", [(16384, 3, 4096, 7, 0, "u", 5), (30000, 3, 900, 7, 11, "u", 1), (20000, 6, 500, 6, 3, "u", 3),
                                              (40000, 2, 800, 5, 1, "g", 2), (60000, 3, 2000, 9, 0, "l", 1), (9000, 1, 9000, 5, 2, "g", 2),
-                                             (12345, 4, 700, 8, 5, "u", 150), (25000, 8, 600, 7, 9, "u", 2)])
+                                             (12345, 4, 700, 8, 5, "u", 150), (25000, 8, 600, 7, 9, "u", 2), (100000, 3, 3000, 7, 4, "u", 2),
+                                             (105000, 2, 1500, 9, 0, "g", 1)])
 def test_group_sampler(n, d, k, h, s, gen, B, oracle):
     """batches of medium clouds on groups of CTAs (kdline_grid_kernel, flat mode: every warp publishes its own keys,
     slices = kd subtrees): more clouds than groups, ties, duplicates, every padded dimension."""
