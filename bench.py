@@ -373,22 +373,23 @@ def gpu_arm(args):
 
 
 def extras(args):
-    """single-cloud latency lines that BASELINE.json's metric also names (ms for 1M -> 64K), device-resident."""
+    """the other BASELINE.json configs next to the headline line, device-resident: ms for the single 1M -> 64K cloud
+    (uniform and lidar-like), the PointNet++ batch (cfg 3), the single 4096-point cloud through both entries."""
     import torch
     from fpsample_b200 import capi
     out = {}
-    for wl, algo, reps in (("cfg4", "kdline", 3), ("cfg4l", "kdline", 3), ("cfg1", "vanilla", 20), ("cfg1", "kdline", 20)):
+    for wl, algo, reps in (("cfg4", "kdline", 3), ("cfg4l", "kdline", 3), ("cfg3", "kdline", 5), ("cfg1", "vanilla", 20), ("cfg1", "kdline", 20)):
         B, n, d, k, h, gen, seed, desc = WORKLOADS[wl]
-        pc = make_cloud(gen, seed, n, d)
+        pc = np.stack([make_cloud(gen, seed + b, n, d) for b in range(B)])
         dp = torch.from_numpy(pc).cuda()
-        do = torch.empty((1, k), dtype=torch.int64, device="cuda")
+        do = torch.empty((B, k), dtype=torch.int64, device="cuda")
         a = capi.ALGO_VANILLA if algo == "vanilla" else capi.ALGO_KDLINE
-        wsb = capi.workspace_bytes(a, 1, n, d, k, h)
+        wsb = capi.workspace_bytes(a, B, n, d, k, h)
         ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda")
         wp = (ws.data_ptr() + 255) & ~255
         st = torch.cuda.current_stream()
-        fn = (lambda: capi.vanilla_batch_dev(dp.data_ptr(), 1, n, d, k, 0, do.data_ptr(), wp, wsb, st.cuda_stream)) if algo == "vanilla" \
-            else (lambda: capi.kdline_batch_dev(dp.data_ptr(), 1, n, d, k, 0, h, do.data_ptr(), wp, wsb, st.cuda_stream))
+        fn = (lambda: capi.vanilla_batch_dev(dp.data_ptr(), B, n, d, k, 0, do.data_ptr(), wp, wsb, st.cuda_stream)) if algo == "vanilla" \
+            else (lambda: capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, do.data_ptr(), wp, wsb, st.cuda_stream))
         fn()
         torch.cuda.synchronize()
         ts = []
@@ -400,7 +401,7 @@ def extras(args):
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
         out[f"{wl}_{algo}"] = {"ms": min(ts), "ms_mean": statistics.mean(ts), "ns_per_pick": min(ts) * 1e6 / max(k - 1, 1),
-                               "what": desc, "plan": capi.last_plan()}
+                               "clouds": B, "clouds_per_s": B / (min(ts) * 1e-3), "what": desc, "plan": capi.last_plan()}
     return out
 
 
