@@ -164,13 +164,16 @@ static int check_kdline(size_t n, size_t dim, size_t h) {
 
 // ---- enqueue on the current device ------------------------------------------------------------------------------
 struct WsLayout {
-    bool cluster;
+    bool cluster, kd;   // kd: big clouds go through a kd permutation + the batched-pick grid sampler (exact, pruned)
+    size_t kd_h, kd_total;
     VanillaPlan vp;
     VanillaGridPlan gp;
     size_t off_scratch, off_slots, off_counters, total;
 };
+static bool vanilla_kd_layout(size_t B, size_t n, size_t dim, size_t n_starts, int n_sms, size_t *h, size_t *total);
 
-static void vanilla_layout(size_t B, size_t n, size_t dim, int n_sms, WsLayout *L) {
+static void vanilla_layout(size_t B, size_t n, size_t dim, int n_sms, WsLayout *L, size_t n_starts = 1) {
+    L->kd = vanilla_kd_layout(B, n, dim, n_starts, n_sms, &L->kd_h, &L->kd_total);
     L->cluster = plan_vanilla_cluster(n, dim, B, n_sms, &L->vp);
     L->off_scratch = L->off_slots = L->off_counters = 0;
     L->total = 256;
@@ -185,12 +188,20 @@ static void vanilla_layout(size_t B, size_t n, size_t dim, int n_sms, WsLayout *
         o += (L->gp.scratch_floats * 4 + 255) & ~(size_t)255;
         L->total = o + 256;
     }
+    if (L->kd && L->kd_total > L->total) L->total = L->kd_total;
 }
+
+static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts, size_t h,
+                          u64 *d_out, u32 *perm_out, u32 *leaf_lo_out, float *leaf_box_out, void *ws,
+                          size_t ws_bytes, int n_sms, cudaStream_t st, const float *van_pts = nullptr, size_t van_nstarts = 1);
 
 static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts,
                            size_t n_starts, u64 *d_out, void *ws, size_t ws_bytes, int n_sms, cudaStream_t st) {
     WsLayout L;
-    vanilla_layout(B, n, dim, n_sms, &L);
+    vanilla_layout(B, n, dim, n_sms, &L, d_starts ? n_starts : 1);
+    if (L.kd)
+        return enqueue_kdline(d_pts, B, n, dim, k, d_starts, L.kd_h, d_out, nullptr, nullptr, nullptr, ws, ws_bytes, n_sms, st,
+                              d_pts, n_starts);
     if (L.cluster) {
         VanillaArgs a;
         a.pts = d_pts;
@@ -244,15 +255,15 @@ struct KdLayout {
     DistPlan dp;
     GridPlan gp;
     bool async, gridbuild, warp, dist, grid;
-    size_t region_off, region_stride, aux_off, counter_off, pub_off, total;
+    size_t region_off, region_stride, aux_off, counter_off, pub_off, qv_off, total;
 };
 
 // fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
 // and sample with the cluster coordinator/worker kernel
-static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L) {
+static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L, bool ids = false) {
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
-    L->region_off = L->region_stride = L->aux_off = L->counter_off = L->pub_off = 0;
+    L->region_off = L->region_stride = L->aux_off = L->counter_off = L->pub_off = L->qv_off = 0;
     L->gridbuild = L->grid = L->dist = L->async = false;
     L->total = L->pl.ws_bytes;
     // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
@@ -265,9 +276,9 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         GridPlan tmp;
         // ... unless the batch is big enough for the one-warp-per-cloud streaming kernel (>= 4 clouds per SM in flight,
         // HBM-bound: BASELINE.json cfg 5) and a cloud would tie up 4 or more SMs
-        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp) && tmp.flat && (tmp.gc <= 2 || B < (size_t)4 * n_sms);
+        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp, ids) && tmp.flat && (ids || tmp.gc <= 2 || B < (size_t)4 * n_sms);
     }
-    L->warp = !build_only && !force_grid && !prefer_group && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
+    L->warp = !build_only && !force_grid && !prefer_group && !ids && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {
         L->async = false;
         L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
@@ -279,7 +290,8 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
     // (kdline_async.cu) covers what is left (2^h > 512 buckets)
     // one huge cloud: the whole GPU samples it, points in shared memory, batched picks (kdline_grid.cu)
-    L->grid = !build_only && (force_grid || prefer_group || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp);
+    L->grid = !build_only && (force_grid || prefer_group || ids || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp, ids);
+    if (ids && !L->grid) return cudaErrorNotSupported;
     L->dist = !build_only && !L->grid && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
     L->async = !build_only && !L->grid && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
     if (L->async || L->dist || L->grid) {
@@ -293,16 +305,41 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         if (L->grid) {
             L->pub_off = (L->total + 255) & ~(size_t)255;
             L->total = L->pub_off + kd_grid_pub_bytes(L->gp);
+            if (ids) {   // the reversed SoA copy of the input
+                L->qv_off = (L->total + 255) & ~(size_t)255;
+                L->total = L->qv_off + B * dim * ((n + 31) & ~(size_t)31) * sizeof(float);
+            }
         }
     }
     return cudaSuccess;
 }
 
+// vanilla FPS on big clouds: the same exact recurrence, pruned.  A kd permutation (height chosen here: leaves of ~128-256
+// points) groups the points into slices; ties are decided by the original index, so the result is fps_sampling's own.
+static bool vanilla_kd_layout(size_t B, size_t n, size_t dim, size_t n_starts, int n_sms, size_t *h, size_t *total) {
+    int want = -1;
+    if (const char *e = getenv("FPS_B200_VANILLA_KD")) want = atoi(e);
+    if (want == 0 || dim > FPS_B200_MAX_KDLINE_DIM || n_starts > 256 || n_starts == 0) return false;
+    if (want < 0 && n < 16384) return false;   // smaller clouds: brute force in registers (vanilla_cluster_kernel) wins
+    if (n < 2048) return false;
+    size_t hh = 1;
+    while (hh < 12 && (n >> hh) > 192) ++hh;
+    if (n >= 262144 && hh > 9) hh = 9;   // one huge cloud on the whole grid: slices are cut inside leaves, few leaves
+    KdLayout L;
+    if (kd_layout(B, n, dim, hh, n_sms, false, &L, true) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    *h = hh;
+    *total = L.total;
+    return true;
+}
+
 static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, size_t k, const u64 *d_starts, size_t h,
                           u64 *d_out, u32 *perm_out, u32 *leaf_lo_out, float *leaf_box_out, void *ws,
-                          size_t ws_bytes, int n_sms, cudaStream_t st) {
+                          size_t ws_bytes, int n_sms, cudaStream_t st, const float *van_pts, size_t van_nstarts) {
     KdLayout L;
-    CK(kd_layout(B, n, dim, h, n_sms, d_out == nullptr, &L));
+    CK(kd_layout(B, n, dim, h, n_sms, d_out == nullptr, &L, van_pts != nullptr));
     const KdlinePlan &pl = L.pl;
     if (!ws || ws_bytes < L.total || (reinterpret_cast<uintptr_t>(ws) & 255)) {
         set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", L.total, ws_bytes);
@@ -341,8 +378,9 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
         tl_phase.mark(0, st);
-        set_plan("%s + kdline_grid_kernel<DIM=%d,%s> clouds=%zu grid=%u (%u CTAs per cloud, %u clouds in flight) threads=1024 "
+        set_plan("%s%s + kdline_grid_kernel<DIM=%d,%s> clouds=%zu grid=%u (%u CTAs per cloud, %u clouds in flight) threads=1024 "
                  "points/thread=%u candidates/round<=%u smem=%zu region/cloud=%zu",
+                 van_pts ? "vanilla FPS via kd permutation (ties by original index): " : "",
                  L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.gp.dimp,
                  L.gp.flat ? "flat" : "merged", B, L.gp.G, L.gp.gc, L.gp.groups, L.gp.ppt, L.gp.ecap, L.gp.smem, L.region_stride);
         if (L.gridbuild)
@@ -351,8 +389,11 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         else
             CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
         tl_phase.mark(1, st);
+        a.starts = van_pts ? nullptr : d_starts;   // (the build kernels never read it)
         CK(launch_kdline_grid(L.gp, a.region, a.region_stride, d_starts, d_out, static_cast<unsigned char *>(ws) + L.pub_off,
-                              (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h, st));
+                              (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h, st, van_pts,
+                              van_pts ? reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + L.qv_off) : nullptr,
+                              (u32)van_nstarts));
         tl_phase.mark(2, st);
         return FPS_OK;
     }

@@ -117,9 +117,12 @@ struct GridPlan {
     size_t smem;
 };
 size_t kd_grid_pub_bytes(const GridPlan &pl);
-bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl);
+bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl, bool ids = false);
+// pts_vanilla != nullptr: vanilla FPS over the same machinery (starts = [B][n_starts] original indices, ties to the highest
+// index); qv = scratch for the reversed SoA copy of the input, B * dim * npad floats
 cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
-                               unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
+                               unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st,
+                               const float *pts_vanilla = nullptr, float *qv = nullptr, u32 n_starts = 1);
 cudaError_t grid_debug_counters(u64 *out16);
 
 // ---- kd-line build with the whole grid per level (kdbuild.cu), into the same per-cloud regions -------------

@@ -64,6 +64,9 @@ struct GridArgs {
     u64 *out;
     uint4 *pub;          // [2][G][G_NK / 2] stamped 16-byte chunks (two 8-byte words each), zeroed before the launch
     u32 B, n, npad, dim, k, ppt, ecap, S, gc;
+    const float *qv;     // IDS: per cloud [dim][npad] coordinates by virtual position (the input reversed, SoA)
+    size_t qv_stride;    // floats
+    u32 n_starts;        // IDS: forced first picks per cloud (original indices), >= 1
 };
 
 // gpu-scope relaxed accesses: served by L2, never by a stale L1 line
@@ -99,7 +102,11 @@ __device__ __forceinline__ u64 key_max(u64 a, u64 b) { return a > b ? a : b; }
 // FLAT = false: one huge cloud on the whole grid, every CTA merges its warps' keys and publishes its 8 largest.
 // FLAT = true : a batch of medium clouds, GROUPS of gc <= 16 CTAs per cloud; every warp publishes its own 3 largest keys
 //               + a bound (no CTA-level merge: with few CTAs per cloud the candidates per round would be too few).
-template <int DIM, bool FLAT>
+// IDS = true  : vanilla FPS (src/lib.cpp:111-246) through the same machinery: the kd permutation only decides which points
+//               share a slice; every point carries a VIRTUAL position n - 1 - original index, so that the lowest virtual
+//               position among equal distances is the HIGHEST original index (the '>=' at lib.cpp:226); coordinates of a
+//               pick are fetched from the reversed input (a.qv), starts are original indices, distances start at +inf.
+template <int DIM, bool FLAT, bool IDS>
 __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const u32 tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -128,7 +135,9 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
     u32 *rowany = pickw + 16;                                                      // [G_ECAP]
     u32 *conf = rowany + G_ECAP;                                                // [G_ECAP][8] conflict bits
     u32 *slt = conf + G_ECAP * 8;                                               // [2][512] flat mode: first position / size of every slice
-    u32 *cum = slt + 1024;                                               // [S + 1] first slice of every leaf
+    u32 *cum = slt + 1024;                                                      // [S + 1] (see below), then IDS: [PCQ] uint4 virtual positions
+    uint4 *pid = reinterpret_cast<uint4 *>((reinterpret_cast<uintptr_t>(cum + S + 1) + 15) & ~(uintptr_t)15);
+    //                                             // [S + 1] first slice of every leaf
     enum { M_NREL = 0, M_STOP = 1, M_J = 2, M_E0 = 4 };
 
     float4 *pv = pts + (size_t)DIM * PCQ;   // running distances; padding slots hold -1 (never a candidate)
@@ -147,6 +156,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
         const u32 *perm = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 1) * npad;
         const u32 *nlo = perm + npad;
         u64 *out = a.out + (size_t)cloud * k;
+        const float *qf = IDS ? a.qv + (size_t)cloud * a.qv_stride : q;   // coordinates by (virtual) position
 
         if (tid < 2 * DIM) cbox[tid] = tid < DIM ? 0x7fffffff : (int)0x80000000;
         u32 wpos0 = 0, wcnt = 0;   // this warp's slice: positions [wpos0, wpos0 + wcnt) of the permuted array
@@ -235,7 +245,13 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                 const u32 l0 = (u * 32u + lane) * 4u;
                 float vv[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) vv[e] = (l0 + e < wcnt) ? FLT_MAX : -1.0f;
+                for (int e = 0; e < 4; ++e) vv[e] = (l0 + e < wcnt) ? (IDS ? __int_as_float(0x7f800000) : FLT_MAX) : -1.0f;
+                if constexpr (IDS) {
+                    u32 id[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) id[e] = (l0 + e < wcnt) ? a.n - 1u - __ldg(perm + wpos0 + l0 + e) : 0u;
+                    pid[slot] = make_uint4(id[0], id[1], id[2], id[3]);
+                }
                 pv[slot] = make_float4(vv[0], vv[1], vv[2], vv[3]);
 #pragma unroll
                 for (int c = 0; c < DIM; ++c) {
@@ -275,16 +291,23 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             for (u32 u = 0; u < NU; ++u) {
                 const float4 v = pv[(warp * NU + u) * 32u + lane];
                 const u32 l0 = wpos0 + (u * 32u + lane) * 4u;
+                uint4 idv = make_uint4(0, 0, 0, 0);
+                if constexpr (IDS) idv = pid[(warp * NU + u) * 32u + lane];
 #pragma unroll
                 for (int e4 = 0; e4 < 4; ++e4) {
                     const float x = f4get(v, e4);
-                    const bool g1 = x > v1, g2 = x > v2, g3 = x > v3;
+                    const u32 px = IDS ? (e4 == 0 ? idv.x : e4 == 1 ? idv.y : e4 == 2 ? idv.z : idv.w) : l0 + e4;
+                    // slots are visited in ascending position: strict '>' keeps the lowest position; virtual positions
+                    // come in no order, so equal distances compare them
+                    const bool g1 = x > v1 || (IDS && x == v1 && x >= 0.0f && px < p1);
+                    const bool g2 = x > v2 || (IDS && x == v2 && x >= 0.0f && px < p2);
+                    const bool g3 = x > v3 || (IDS && x == v3 && x >= 0.0f && px < p3);
                     v3 = g2 ? v2 : (g3 ? x : v3);
-                    p3 = g2 ? p2 : (g3 ? l0 + e4 : p3);
+                    p3 = g2 ? p2 : (g3 ? px : p3);
                     v2 = g1 ? v1 : (g2 ? x : v2);
-                    p2 = g1 ? p1 : (g2 ? l0 + e4 : p2);
+                    p2 = g1 ? p1 : (g2 ? px : p2);
                     v1 = g1 ? x : v1;
-                    p1 = g1 ? l0 + e4 : p1;
+                    p1 = g1 ? px : p1;
                 }
             }
             u64 k1 = v1 < 0.0f ? 0ull : make_key(v1, G_LOW - p1), k2 = v2 < 0.0f ? 0ull : make_key(v2, G_LOW - p2),
@@ -314,13 +337,18 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
 
         // ---- the first pick: the point at POSITION start (wrapper.hpp:54-55) ------------------------------------------
         if (tid == 0) {
-            const u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;
-            tpos[0] = cur;
-            tval[0] = FLT_MAX;
-            for (u32 c = 0; c < DIM; ++c) tc[c * G_ECAP] = c < dim ? __ldg(q + (size_t)c * npad + cur) : 0.0f;
-            rel[0] = 0;
-            misc[M_NREL] = 1;
-            if (cta == 0) out[0] = (u64)cur;   // positions now, original ids by grid_map_kernel at the end
+            // kd-line: the point at POSITION start; vanilla: the forced start indices, in order (lib.cpp:151-155)
+            const u32 ns = IDS ? a.n_starts : 1u;
+            for (u32 i = 0; i < ns; ++i) {
+                u32 cur = a.starts ? (u32)a.starts[(size_t)cloud * ns + i] : 0u;
+                if constexpr (IDS) cur = a.n - 1u - cur;
+                tpos[i] = cur;
+                tval[i] = FLT_MAX;
+                for (u32 c = 0; c < DIM; ++c) tc[c * G_ECAP + i] = c < dim ? __ldg(qf + (size_t)c * npad + cur) : 0.0f;
+                rel[i] = i;
+                if (cta == 0) out[i] = (u64)cur;   // positions now, original ids by grid_map_kernel at the end
+            }
+            misc[M_NREL] = ns;
         }
         reselect();          // every valid point is at FLT_MAX: smax = FLT_MAX, so the first pick touches every slice
         __syncthreads();
@@ -331,7 +359,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
             chi[c] = c < (int)dim ? ord2f(cbox[DIM + c]) : 0.0f;
         }
 
-        u32 t = 1;
+        u32 t = IDS ? a.n_starts : 1u;
 #pragma unroll 1
         while (t < k) {
             const long long c0 = GCLK();
@@ -559,7 +587,7 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
                     if (part == 0) {
 #pragma unroll
                         for (int c = 0; c < DIM; ++c)
-                            if (c < (int)dim) cc[c] = __ldg(q + (size_t)c * npad + pos);
+                            if (c < (int)dim) cc[c] = __ldg(qf + (size_t)c * npad + pos);
                     }
                     u32 cn = 0;
 #pragma unroll 2
@@ -749,11 +777,26 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
 }
 
 // positions -> original ids (src/wrapper.hpp:57-59), after the sampling kernel
-__global__ void grid_map_kernel(u64 *out, const unsigned char *region, size_t region_stride, u32 B, u32 k, u32 dim, u32 npad) {
+__global__ void grid_map_kernel(u64 *out, const unsigned char *region, size_t region_stride, u32 B, u32 k, u32 dim, u32 npad,
+                                u32 n_virtual) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)B * k) return;
+    if (n_virtual) {   // vanilla: virtual position -> original index
+        out[i] = (u64)(n_virtual - 1u - (u32)out[i]);
+        return;
+    }
     const u32 *perm = reinterpret_cast<const u32 *>(region + (i / k) * region_stride) + (size_t)(dim + 1) * npad;
     out[i] = (u64)__ldg(perm + (u32)out[i]);
+}
+
+// vanilla: qv[c][vp] = pts[n - 1 - vp][c]
+__global__ void grid_reverse_kernel(const float *pts, float *qv, size_t qv_stride, u32 B, u32 n, u32 dim, u32 npad) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)B * n * dim) return;
+    const u32 b = (u32)(i / ((size_t)n * dim));
+    const size_t f = i - (size_t)b * n * dim;
+    const u32 p = (u32)(f / dim), c = (u32)(f - (size_t)p * dim);
+    qv[(size_t)b * qv_stride + (size_t)c * npad + (n - 1u - p)] = pts[i];
 }
 
 // ======================================================================================================
@@ -761,14 +804,15 @@ __global__ void grid_map_kernel(u64 *out, const unsigned char *region, size_t re
 // ======================================================================================================
 static int pad_dim_g(int dim) { return dim <= 2 ? 2 : dim == 3 ? 3 : dim == 4 ? 4 : dim <= 6 ? 6 : 8; }
 
-static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat, u32 gc = 16) {
+static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat, u32 gc = 16, bool ids = false) {
     const size_t pcq = (size_t)G_W * (ppt / 4) * 32;
     size_t b = (size_t)(dimp + 1) * pcq * 16;            // points
     b += flat ? (size_t)gc * G_W * 4 * 8 : (size_t)G_MAXG * G_NK * 8;  // gathered keys
     b += G_W * 4 * 8 + 2 * G_ECAP * 8 + 32 * 8;          // wtop, ekey, red
     b += (size_t)G_ECAP * 4 * 2;                         // tpos, tval
     b += (size_t)dimp * G_ECAP * 4 + G_ECAP * 4;         // tc, rel
-    b += 2 * dimp * 4 + 16 * 4 + 16 * 4 + (S + 1) * 4;   // cbox, misc, wflag, cum
+    b += 2 * dimp * 4 + 16 * 4 + 16 * 4 + ((S + 1 + 3) & ~(size_t)3) * 4;   // cbox, misc, wflag, cum
+    if (ids) b += pcq * 16 + 16;                          // virtual positions
     b += 32 * 4 + G_ECAP * 4 + G_ECAP * 8 * 4 + 1024 * 4;// lw, pickw, rowany, conf, slt
     return (b + 15) & ~(size_t)15;
 }
@@ -777,7 +821,7 @@ size_t kd_grid_pub_bytes(const GridPlan &pl) {
     return pl.flat ? (size_t)pl.groups * 2 * pl.gc * G_W * 4 * 8 : (size_t)2 * G_MAXG * G_NK * 8;
 }
 
-bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl) {
+bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl, bool ids) {
     if (dim == 0 || dim > 8 || h == 0 || n == 0 || B == 0 || n >= G_PNONE) return false;
     int want = -1;
     if (const char *e = getenv("FPS_B200_GRID")) want = atoi(e);
@@ -802,7 +846,7 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
         for (u32 p = 12; p >= 4; p -= 4) {
             const size_t per_cta = (size_t)G_T * p;
             for (u32 gc = 1; gc <= 16; gc *= 2) {
-                if (grid_smem(dimp, p, S, true, gc) > 227 * 1024) break;
+                if (grid_smem(dimp, p, S, true, gc, ids) > 227 * 1024) break;
                 // room for the subtree packing: ~20 % slack (a tighter fit falls back to position ranges in the kernel)
                 if (gc * per_cta * 5 < n * 6) continue;
                 if (gc > sms) break;
@@ -814,7 +858,7 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
                 pl->groups = (u32)groups;
                 pl->G = (u32)(groups * gc);
                 pl->flat = 1;
-                pl->smem = grid_smem(dimp, p, S, true, gc);
+                pl->smem = grid_smem(dimp, p, S, true, gc, ids);
                 return true;
             }
         }
@@ -826,7 +870,7 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
     for (u32 p = 4; p <= 16 && !ppt; p += 4) {
         const size_t SL = 32 * (size_t)p, slices = (n + SL - 1) / SL + S;
         const size_t g = (slices + G_W - 1) / G_W;
-        if (g <= sms && grid_smem(dimp, p, S, false) <= 227 * 1024) {
+        if (g <= sms && grid_smem(dimp, p, S, false, 16, ids) <= 227 * 1024) {
             ppt = p;
             G = (u32)g;
         }
@@ -837,13 +881,13 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
     pl->gc = G;
     pl->groups = 1;
     pl->flat = 0;
-    pl->smem = grid_smem(dimp, ppt, S, false);
+    pl->smem = grid_smem(dimp, ppt, S, false, 16, ids);
     return true;
 }
 
-template <int DIM, bool FLAT>
+template <int DIM, bool FLAT, bool IDS>
 static cudaError_t launch_grid_t(const GridPlan &pl, GridArgs &a, cudaStream_t st) {
-    auto kern = kdline_grid_kernel<DIM, FLAT>;
+    auto kern = kdline_grid_kernel<DIM, FLAT, IDS>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     void *params[] = {&a};
@@ -877,8 +921,20 @@ cudaError_t grid_debug_counters(u64 *out16) {
     return cudaMemcpyFromSymbol(out16, g_grid_dbg, sizeof(u64) * 16);
 }
 
+template <bool FLAT, bool IDS>
+static cudaError_t launch_grid_d(const GridPlan &pl, GridArgs &a, cudaStream_t st) {
+    switch (pl.dimp) {
+        case 2: return launch_grid_t<2, FLAT, IDS>(pl, a, st);
+        case 3: return launch_grid_t<3, FLAT, IDS>(pl, a, st);
+        case 4: return launch_grid_t<4, FLAT, IDS>(pl, a, st);
+        case 6: return launch_grid_t<6, FLAT, IDS>(pl, a, st);
+        default: return launch_grid_t<8, FLAT, IDS>(pl, a, st);
+    }
+}
+
 cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
-                               unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st) {
+                               unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st, const float *pts_vanilla,
+                               float *qv, u32 n_starts) {
     GridArgs a;
     a.S = 1u << h;
     a.region = region;
@@ -894,29 +950,23 @@ cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t
     a.ppt = pl.ppt;
     a.ecap = pl.ecap;
     a.gc = pl.gc;
+    const bool ids = pts_vanilla != nullptr;
+    a.qv = qv;
+    a.qv_stride = (size_t)dim * a.npad;
+    a.n_starts = n_starts ? n_starts : 1;
     cudaError_t e = cudaMemsetAsync(pub, 0, kd_grid_pub_bytes(pl), st);
     if (e != cudaSuccess) return e;
-    if (pl.flat) {
-        switch (pl.dimp) {
-            case 2: e = launch_grid_t<2, true>(pl, a, st); break;
-            case 3: e = launch_grid_t<3, true>(pl, a, st); break;
-            case 4: e = launch_grid_t<4, true>(pl, a, st); break;
-            case 6: e = launch_grid_t<6, true>(pl, a, st); break;
-            default: e = launch_grid_t<8, true>(pl, a, st); break;
-        }
-    } else {
-        switch (pl.dimp) {
-            case 2: e = launch_grid_t<2, false>(pl, a, st); break;
-            case 3: e = launch_grid_t<3, false>(pl, a, st); break;
-            case 4: e = launch_grid_t<4, false>(pl, a, st); break;
-            case 6: e = launch_grid_t<6, false>(pl, a, st); break;
-            default: e = launch_grid_t<8, false>(pl, a, st); break;
-        }
+    if (ids) {
+        const size_t tot = (size_t)B * n * dim;
+        grid_reverse_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(pts_vanilla, qv, a.qv_stride, B, n, dim, a.npad);
+        count_launch();
     }
+    if (pl.flat) e = ids ? launch_grid_d<true, true>(pl, a, st) : launch_grid_d<true, false>(pl, a, st);
+    else e = ids ? launch_grid_d<false, true>(pl, a, st) : launch_grid_d<false, false>(pl, a, st);
     count_launch();
     if (e != cudaSuccess) return e;
     const size_t tot = (size_t)B * k;
-    grid_map_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(out, region, region_stride, B, k, dim, a.npad);
+    grid_map_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(out, region, region_stride, B, k, dim, a.npad, ids ? n : 0u);
     count_launch();
     return cudaGetLastError();
 }

@@ -248,6 +248,38 @@ def test_group_sampler(n, d, k, h, s, gen, B, oracle):
         os.environ.pop("FPS_B200_GROUP", None)
 
 
+@pytest.mark.parametrize("n,d,k,starts,gen", [(20000, 3, 700, [5, 1, 9], "g"), (16384, 2, 5000, [16383], "g"), (70000, 1, 2000, [0], "g"),
+                                              (30000, 6, 1500, [7, 7, 29999], "u"), (40000, 8, 500, [3], "u"), (300000, 3, 3000, [11], "l"),
+                                              (17000, 3, 17000, [4], "g")])
+def test_vanilla_kd_route(n, d, k, starts, gen, oracle):
+    """fps_sampling on big clouds runs the same exact recurrence pruned by a kd permutation (kdline_grid_kernel, IDS mode):
+    ties still go to the highest ORIGINAL index, start lists are forced in order, k = n drives every distance to 0."""
+    pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=17),
+          "l": lambda: synth.lidar(n, n)}[gen]()
+    got = capi.vanilla(pc, k, starts)
+    assert "vanilla FPS via kd permutation" in capi.last_plan(), capi.last_plan()
+    if n * k <= 3e8:
+        np.testing.assert_array_equal(got, oracle.fps_vanilla(pc, k, starts), err_msg=capi.last_plan())
+    else:
+        ok, where = oracle.certify_vanilla(pc, got, n_forced=len(starts))
+        assert ok, f"first bad round {where} ({capi.last_plan()})"
+    os.environ["FPS_B200_VANILLA_KD"] = "0"   # and the brute-force kernels still agree
+    try:
+        np.testing.assert_array_equal(capi.vanilla(pc, min(k, 300), starts), got[:min(k, 300)])
+        assert "kd permutation" not in capi.last_plan()
+    finally:
+        os.environ.pop("FPS_B200_VANILLA_KD", None)
+
+
+def test_vanilla_kd_batch_with_starts(oracle):
+    pcs = synth.uniform_batch(9100, 7, 20000, 3)
+    st = (np.arange(7) * 2999) % 20000
+    got = capi.vanilla_batch(pcs, 600, st, devices=[0])
+    assert "vanilla FPS via kd permutation" in capi.last_plan(), capi.last_plan()
+    for b in range(7):
+        np.testing.assert_array_equal(got[b], oracle.fps_vanilla(pcs[b], 600, int(st[b])))
+
+
 def test_unaligned_and_strided_inputs(oracle):
     buf = synth.uniform(3, 4097 * 3 + 1, 1).ravel()
     pc = buf[1:1 + 4097 * 3].reshape(4097, 3)           # base address 4 bytes off any 16-byte boundary
