@@ -818,7 +818,7 @@ static size_t grid_smem(int dimp, u32 ppt, size_t S, bool flat, u32 gc = 16, boo
 }
 
 size_t kd_grid_pub_bytes(const GridPlan &pl) {
-    return pl.flat ? (size_t)pl.groups * 2 * pl.gc * G_W * 4 * 8 : (size_t)2 * G_MAXG * G_NK * 8;
+    return pl.flat ? (size_t)pl.groups * 2 * pl.gc * G_W * 4 * 8 : (size_t)pl.groups * 2 * G_MAXG * G_NK * 8;
 }
 
 bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl, bool ids) {
@@ -864,7 +864,6 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
         }
         if (grp == 1) return false;
     }
-    if (want < 0 && (n < 262144 || B > 4)) return false;   // one huge cloud at a time; batches go to the other samplers
     // slices never straddle a leaf: at most ceil(n / SL) + S of them (every leaf ends with one partial slice)
     u32 ppt = 0, G = 0;
     for (u32 p = 4; p <= 16 && !ppt; p += 4) {
@@ -876,10 +875,16 @@ bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridP
         }
     }
     if (!ppt) return false;
+    // a few huge clouds: as many at once as whole groups of G CTAs fit; measured against the cluster coordinator/worker
+    // kernel (scripts/cmp_mid.py) it wins from ~130 k points as long as the batch needs at most two passes
+    size_t groups = sms / G;
+    if (groups > B) groups = B;
+    if (groups < 1) groups = 1;
+    if (want < 0 && (n < 131072 || (B + groups - 1) / groups > 2)) return false;
     pl->ppt = ppt;
-    pl->G = G;
+    pl->G = (u32)(groups * G);
     pl->gc = G;
-    pl->groups = 1;
+    pl->groups = (u32)groups;
     pl->flat = 0;
     pl->smem = grid_smem(dimp, ppt, S, false, 16, ids);
     return true;
