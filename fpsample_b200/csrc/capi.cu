@@ -254,7 +254,8 @@ struct KdLayout {
     WarpPlan wp;
     DistPlan dp;
     GridPlan gp;
-    bool async, gridbuild, warp, dist, grid;
+    KdSmallPlan sp;
+    bool async, gridbuild, warp, dist, grid, small;
     size_t region_off, region_stride, aux_off, counter_off, pub_off, qv_off, total;
 };
 
@@ -264,7 +265,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
     L->region_off = L->region_stride = L->aux_off = L->counter_off = L->pub_off = L->qv_off = 0;
-    L->gridbuild = L->grid = L->dist = L->async = false;
+    L->gridbuild = L->grid = L->dist = L->async = L->small = false;
     L->total = L->pl.ws_bytes;
     // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
     bool force_grid = false;   // tests force the whole-GPU sampler onto clouds the planner would keep on one SM
@@ -281,6 +282,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     L->warp = !build_only && !force_grid && !prefer_group && !ids && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {
         L->async = false;
+        L->small = plan_kdsmall(n, dim, h, B, n_sms, &L->sp);   // the build that feeds the regions
         L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
         L->region_stride = kd_region_bytes(n, dim, h);
         L->counter_off = L->region_off + B * L->region_stride;
@@ -361,12 +363,20 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     if (L.warp) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
-        set_plan("kdline_kernel(build, 1 CTA per cloud) + kdline_warp%s_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
+        char bdesc[96];
+        if (L.small)
+            snprintf(bdesc, sizeof bdesc, "kdsmall_kernel<DIM=%d>(build in shared memory, %u CTAs per SM, smem=%zu)", L.sp.dimp, L.sp.occ, L.sp.smem);
+        else
+            snprintf(bdesc, sizeof bdesc, "kdline_kernel(build, 1 CTA per cloud)");
+        set_plan("%s + kdline_warp%s_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
                  "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
-                 L.wp.global ? "g" : (L.wp.hybrid ? "(hybrid smem+tmem)" : ""), L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
+                 bdesc, L.wp.global ? "g" : (L.wp.hybrid ? "(hybrid smem+tmem)" : ""), L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
                  L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
         tl_phase.mark(0, st);
-        CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (L.small)
+            CK(launch_kdsmall(L.sp, d_pts, a.region, a.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
+        else
+            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
         tl_phase.mark(1, st);
         CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
                               reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,

@@ -74,6 +74,17 @@ struct KdlinePlan {
 cudaError_t plan_kdline(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdlinePlan *pl);
 cudaError_t launch_kdline(const KdlinePlan &pl, KdlineArgs a, unsigned char *ws_base, cudaStream_t st);
 
+// ---- kd-line build for batches of small clouds, everything in one CTA's shared memory (kdsmall.cu) --------
+struct KdSmallPlan {
+    int dimp;
+    u32 grid, occ;
+    size_t smem;
+};
+bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPlan *pl);
+// counter: 256 zero-able bytes of workspace (dynamic cloud scheduler)
+cudaError_t launch_kdsmall(const KdSmallPlan &pl, const float *pts, unsigned char *region, size_t region_stride,
+                           u32 *counter, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
+
 // ---- kd-line, asynchronous coordinator/worker sampling over prebuilt regions (kdline_async.cu) -----------
 // per-cloud region: [q dim*npad f32][dis npad f32][perm npad u32][nlo pad32(S+1) u32][fbox S*2*dim f32]
 size_t kd_region_bytes(size_t n, size_t dim, size_t h);
