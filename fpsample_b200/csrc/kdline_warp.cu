@@ -18,6 +18,7 @@
 // always allowed.  Float rounding is monotone, so skipped work never changes a distance and the result equals the
 // eager recurrence bit for bit (tests/test_oracle.py::test_lazy_equals_eager, GPU parity suite).
 #include <cfloat>
+#include <type_traits>
 
 #include "common.cuh"
 #include "engine.h"
@@ -55,6 +56,15 @@ __device__ __forceinline__ void sts128(u32 a, float x, float y, float z, float w
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
 }
 
+__device__ __forceinline__ float2 lds64(u32 a) {
+    float2 f;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f.x), "=f"(f.y) : "r"(a));
+    return f;
+}
+__device__ __forceinline__ void sts64(u32 a, float x, float y) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory");
+}
+
 // ---- the two point stores ---------------------------------------------------------------------------------------
 // component c (0..DIM-1 coordinates, DIM = running distance) of position (chunk, lane)
 struct SmemStore {
@@ -62,17 +72,32 @@ struct SmemStore {
     u32 base;   // shared-space byte address of this warp's slot
     u32 lst;    // words per (component, lane) row: nch + 4 (16-byte aligned rows, conflict-free 128-bit access)
     __device__ __forceinline__ u32 addr(u32 comp, u32 lane, u32 chunk) const { return base + ((comp * 32u + lane) * lst + chunk) * 4u; }
-    // 8 consecutive chunks starting at a multiple of 4
-    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
+    // U consecutive chunks: 8 start at a multiple of 4 (two 128-bit accesses), 4 and 6 at an even chunk (64-bit accesses)
+    template <int U>
+    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
         const u32 a = addr(comp, lane, cb);
-        const float4 f0 = lds128(a), f1 = lds128(a + 16u);
-        v[0] = f0.x, v[1] = f0.y, v[2] = f0.z, v[3] = f0.w, v[4] = f1.x, v[5] = f1.y, v[6] = f1.z, v[7] = f1.w;
+        if constexpr (U == 8) {
+            const float4 f0 = lds128(a), f1 = lds128(a + 16u);
+            v[0] = f0.x, v[1] = f0.y, v[2] = f0.z, v[3] = f0.w, v[4] = f1.x, v[5] = f1.y, v[6] = f1.z, v[7] = f1.w;
+        } else {
+#pragma unroll
+            for (int i = 0; i < U; i += 2) {
+                const float2 f = lds64(a + 4u * i);
+                v[i] = f.x, v[i + 1] = f.y;
+            }
+        }
     }
     __device__ __forceinline__ void wait_ld() const {}
-    __device__ __forceinline__ void store8(u32 comp, u32 lane, u32 cb, const float (&v)[W_U]) const {
+    template <int U>
+    __device__ __forceinline__ void store(u32 comp, u32 lane, u32 cb, const float (&v)[U]) const {
         const u32 a = addr(comp, lane, cb);
-        sts128(a, v[0], v[1], v[2], v[3]);
-        sts128(a + 16u, v[4], v[5], v[6], v[7]);
+        if constexpr (U == 8) {
+            sts128(a, v[0], v[1], v[2], v[3]);
+            sts128(a + 16u, v[4], v[5], v[6], v[7]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < U; i += 2) sts64(a + 4u * i, v[i], v[i + 1]);
+        }
     }
     __device__ __forceinline__ void wait_st() const {}
     // coordinates of position p, to every lane
@@ -87,21 +112,47 @@ struct TmemStore {
     static constexpr bool kTrackCoords = false;
     u32 base;   // tensor-memory address of this warp's lane quarter: (32 * (warp % 4)) << 16 | first column
     u32 nch;    // columns per component
-    __device__ __forceinline__ void load8(u32 comp, u32, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
-        u32 w[W_U];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
-                     : "r"(base + comp * nch + cb)
+    __device__ __forceinline__ void ld4(u32 col, u32 *w) const {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(col) : "memory");
+    }
+    __device__ __forceinline__ void st4(u32 col, const float *v) const {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(col), "r"(__float_as_uint(v[0])),
+                     "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                      : "memory");
+    }
+    template <int U>
+    __device__ __forceinline__ void load(u32 comp, u32, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
+        u32 w[U];
+        const u32 col = base + comp * nch + cb;
+        if constexpr (U == 8) {
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                         : "r"(col)
+                         : "memory");
+        } else {
+            ld4(col, w);
+            if constexpr (U == 6)
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(w[4]), "=r"(w[5]) : "r"(col + 4u) : "memory");
+        }
 #pragma unroll
-        for (int i = 0; i < W_U; ++i) v[i] = __uint_as_float(w[i]);
+        for (int i = 0; i < U; ++i) v[i] = __uint_as_float(w[i]);
     }
     __device__ __forceinline__ void wait_ld() const { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-    __device__ __forceinline__ void store8(u32 comp, u32, u32 cb, const float (&v)[W_U]) const {
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(base + comp * nch + cb),
-                     "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
-                     "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-                     : "memory");
+    template <int U>
+    __device__ __forceinline__ void store(u32 comp, u32, u32 cb, const float (&v)[U]) const {
+        const u32 col = base + comp * nch + cb;
+        if constexpr (U == 8) {
+            asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(col),
+                         "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+                         "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+                         : "memory");
+        } else {
+            st4(col, v);
+            if constexpr (U == 6)
+                asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(col + 4u), "r"(__float_as_uint(v[4])),
+                             "r"(__float_as_uint(v[5]))
+                             : "memory");
+        }
     }
     __device__ __forceinline__ void wait_st() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
     // the point lives in lane p % 32 of this warp's quarter: every lane reads its own column, the owner broadcasts
@@ -125,14 +176,16 @@ struct HybridStore {
     SmemStore s;   // DIM components
     TmemStore t;   // one component: the distance of chunk c is column c
     u32 dimc;      // index of the distance component (= DIM of the kernel)
-    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 = 0, bool = false) const {
-        if (comp == dimc) t.load8(0, lane, cb, v);
-        else s.load8(comp, lane, cb, v);
+    template <int U>
+    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
+        if (comp == dimc) t.load<U>(0, lane, cb, v);
+        else s.load<U>(comp, lane, cb, v);
     }
     __device__ __forceinline__ void wait_ld() const { t.wait_ld(); }
-    __device__ __forceinline__ void store8(u32 comp, u32 lane, u32 cb, const float (&v)[W_U]) const {
-        if (comp == dimc) t.store8(0, lane, cb, v);
-        else s.store8(comp, lane, cb, v);
+    template <int U>
+    __device__ __forceinline__ void store(u32 comp, u32 lane, u32 cb, const float (&v)[U]) const {
+        if (comp == dimc) t.store<U>(0, lane, cb, v);
+        else s.store<U>(comp, lane, cb, v);
     }
     __device__ __forceinline__ void wait_st() const { t.wait_st(); }
     template <int DIM>
@@ -150,9 +203,10 @@ struct GlobalStore {
     float *dis;       // [npad]
     u32 npad, n;
     // comp < ncomp: a coordinate; ncomp <= comp < DIM (padding dims of the template): 0; comp == DIM: the distance
-    __device__ __forceinline__ void load8(u32 comp, u32 lane, u32 cb, float (&v)[W_U], u32 ncomp, bool is_dis) const {
+    template <int U>
+    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 ncomp, bool is_dis) const {
 #pragma unroll
-        for (int u = 0; u < W_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const u32 p = (cb + u) * 32 + lane;
             v[u] = 0.0f;
             if (p < n) {
@@ -162,9 +216,10 @@ struct GlobalStore {
         }
     }
     __device__ __forceinline__ void wait_ld() const {}
-    __device__ __forceinline__ void store8(u32, u32 lane, u32 cb, const float (&v)[W_U]) const {   // distances only
+    template <int U>
+    __device__ __forceinline__ void store(u32, u32 lane, u32 cb, const float (&v)[U]) const {   // distances only
 #pragma unroll
-        for (int u = 0; u < W_U; ++u) {
+        for (int u = 0; u < U; ++u) {
             const u32 p = (cb + u) * 32 + lane;
             if (p < n) __stcg(dis + p, v[u]);
         }
@@ -214,7 +269,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 const u32 p = (cb + u) * 32 + lane;
                 v[u] = (c == DIM) ? FLT_MAX : ((c < (int)dim && p < n) ? __ldg(q + (size_t)c * npad + p) : 0.0f);
             }
-            st.store8(c, lane, cb, v);
+            st.template store<W_U>(c, lane, cb, v);
         }
     }
     for (u32 s = lane; s <= S; s += 32) nlo_s[s] = nlo[s];
@@ -304,15 +359,16 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             float bc[DIM];   // coordinates of this lane's best point (global store only)
 #pragma unroll
             for (int c = 0; c < DIM; ++c) bc[c] = 0.0f;
-            for (u32 cb0 = (lo >> 5) & ~3u; cb0 <= c1b; cb0 += W_U) {
-                const u32 cb = min(cb0, nch - W_U);
-                float x[DIM][W_U], v[W_U], old[W_U];
+            // one straight-line block of U chunks (U x 32 positions): all pending samples applied, first maximum per lane
+            auto block = [&](auto Uc, const u32 cb) {
+                constexpr int U = decltype(Uc)::value;
+                float x[DIM][U], v[U], old[U];
 #pragma unroll
-                for (int c = 0; c < DIM; ++c) st.load8(c, lane, cb, x[c], dim, false);
-                st.load8(DIM, lane, cb, old, dim, true);
+                for (int c = 0; c < DIM; ++c) st.template load<U>(c, lane, cb, x[c], dim, false);
+                st.template load<U>(DIM, lane, cb, old, dim, true);
                 st.wait_ld();
 #pragma unroll
-                for (int u = 0; u < W_U; ++u) v[u] = old[u];
+                for (int u = 0; u < U; ++u) v[u] = old[u];
 #if WDBG
                 dbg[6] += nref;
 #endif
@@ -329,7 +385,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
 #pragma unroll
                     for (int c = 0; c < DIM; ++c) ref[c] = w[c];
 #pragma unroll
-                    for (int u = 0; u < W_U; ++u) {
+                    for (int u = 0; u < U; ++u) {
                         float pt[DIM];
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) pt[c] = x[c][u];
@@ -338,7 +394,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 }
                 // positions outside [lo, hi) belong to a neighbour bucket (or are padding): they keep their value
 #pragma unroll
-                for (int u = 0; u < W_U; ++u) {
+                for (int u = 0; u < U; ++u) {
                     const u32 p = (cb + u) * 32 + lane;
                     const bool in = (p - lo) < span;
                     v[u] = in ? v[u] : old[u];
@@ -351,7 +407,17 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                         }
                     }
                 }
-                st.store8(DIM, lane, cb, v);
+                st.template store<U>(DIM, lane, cb, v);
+            };
+            // the bucket's chunks from an even chunk on (64-bit aligned rows): most buckets of ~128 points fit 6 chunks,
+            // small ones 4; nch is a multiple of 8, so a block pulled back from the end stays aligned
+            const u32 c0 = (lo >> 5) & ~1u, ncn = c1b - c0 + 1;
+            if (ncn <= 4) {
+                block(std::integral_constant<int, 4>{}, min(c0, nch - 4u));
+            } else if (ncn <= 6) {
+                block(std::integral_constant<int, 6>{}, min(c0, nch - 6u));
+            } else {
+                for (u32 cb0 = c0 & ~3u; cb0 <= c1b; cb0 += W_U) block(std::integral_constant<int, W_U>{}, min(cb0, nch - W_U));
             }
             st.wait_st();   // a neighbouring bucket may share this bucket's first / last chunk
             // bucket max, then its lowest position; the owner lane takes both plus the point's coordinates
