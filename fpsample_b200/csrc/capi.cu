@@ -89,6 +89,7 @@ struct DevCtx {
     int dev = -1, n_sms = 0;
     std::mutex mu;
     Lane lane[2];
+    cudaEvent_t ev[8] = {};   // upload-chunk-landed events of the pipelined kd-line path
     bool ready = false;
 };
 
@@ -514,6 +515,7 @@ static int run_shard(int dev, const ShardJob &j) {
     CK(cudaSetDevice(dev));
     if (!cx->ready) {
         for (auto &ln : cx->lane) CK(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        for (auto &e : cx->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         cx->ready = true;
     }
     const size_t in_per = j.n * j.dim * sizeof(float), out_per = j.k * sizeof(u64);
@@ -529,6 +531,57 @@ static int run_shard(int dev, const ShardJob &j) {
     const size_t chunk = (j.B + nch - 1) / nch;
     static_assert(sizeof(size_t) == sizeof(u64), "size_t must be 64-bit");
     int rc = FPS_OK;
+    // One batch of small clouds (the on-chip sampler wants all of them in one launch): the upload is cut into pieces and
+    // every piece is BUILT (kdsmall_kernel, into its clouds' regions) while the next one is still crossing PCIe; the
+    // sampler then runs once over the whole batch.  Copy engine on lane 0's stream, kernels on lane 1's.
+    if (j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && !getenv("FPS_B200_NO_PIPE")) {
+        KdLayout L;
+        CK(kd_layout(j.B, j.n, j.dim, j.h, cx->n_sms, false, &L));
+        if (L.warp && L.small) {
+            Lane &cp = cx->lane[0], &ex = cx->lane[1];
+            if ((rc = cp.in.ensure(j.B * in_per)) || (rc = cp.out.ensure(j.B * out_per)) || (rc = cp.ws.ensure(L.total))) return rc;
+            u64 *d_starts = nullptr;
+            if (j.start) {
+                if ((rc = cp.starts.ensure(j.B * sizeof(u64)))) return rc;
+                d_starts = static_cast<u64 *>(cp.starts.p);
+                CK(cudaMemcpyAsync(d_starts, j.start, j.B * sizeof(u64), cudaMemcpyHostToDevice, ex.st));
+            }
+            unsigned char *ws = static_cast<unsigned char *>(cp.ws.p);
+            unsigned char *region = ws + L.region_off;
+            const float *d_in = static_cast<const float *>(cp.in.p);
+            size_t np = (j.B * in_per) / ((size_t)6 << 20);   // pieces of >= 6 MB
+            if (np < 2) np = 2;
+            if (np > 8) np = 8;
+            const size_t per = (j.B + np - 1) / np;
+            size_t c = 0;
+            for (size_t b0 = 0; b0 < j.B; b0 += per, ++c) {
+                const size_t nb = (j.B - b0 < per) ? j.B - b0 : per;
+                CK(cudaMemcpyAsync(const_cast<float *>(d_in) + b0 * j.n * j.dim, j.pts + b0 * j.n * j.dim, nb * in_per,
+                                   cudaMemcpyHostToDevice, cp.st));
+                CK(cudaEventRecord(cx->ev[c], cp.st));
+                CK(cudaStreamWaitEvent(ex.st, cx->ev[c], 0));
+                KdSmallPlan sp = L.sp;
+                const size_t gmax = (size_t)sp.occ * (size_t)cx->n_sms;
+                sp.grid = (u32)(nb < gmax ? nb : gmax);
+                CK(launch_kdsmall(sp, d_in + b0 * j.n * j.dim, region + b0 * L.region_stride, L.region_stride,
+                                  reinterpret_cast<u32 *>(ws), (u32)nb, (u32)j.n, (u32)j.dim, (u32)j.h, ex.st));
+            }
+            CK(launch_kdline_warp(L.wp, region, L.region_stride, d_starts, static_cast<u64 *>(cp.out.p),
+                                  reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
+                                  ex.st));
+            CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
+            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + kdline_warp_kernel<DIM=%d,BPL=%u> clouds=%zu grid=%u",
+                     c, L.sp.dimp, L.wp.dimp, L.wp.bpl, j.B, L.wp.grid);
+            for (auto &ln : cx->lane) {
+                cudaError_t e = cudaStreamSynchronize(ln.st);
+                if (e != cudaSuccess && rc == FPS_OK) {
+                    set_err("kernel execution failed: %s", cudaGetErrorString(e));
+                    rc = FPS_ERR_CUDA + (int)e;
+                }
+            }
+            return rc;
+        }
+    }
     for (size_t c = 0, b0 = 0; b0 < j.B && rc == FPS_OK; ++c, b0 += chunk) {
         const size_t nb = (j.B - b0 < chunk) ? j.B - b0 : chunk;
         Lane &ln = cx->lane[c & 1];

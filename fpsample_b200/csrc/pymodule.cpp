@@ -6,6 +6,8 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <map>
+#include <mutex>
 #include <optional>
 #include <string>
 #include <vector>
@@ -122,6 +124,65 @@ static py::array_t<size_t> kdtree_py(farray points, size_t n_samples, py::object
 }
 
 // ---- batched entries (new) -----------------------------------------------------------------------------
+// Large index arrays are handed out over page-locked memory from the library (fps_b200_host_alloc): the device-to-host
+// copy then runs at PCIe speed straight into the array the caller gets, with no pageable bounce buffer and no first-touch
+// page faults.  A buffer goes back to a small free list when its array (and every view of it) is collected, so a
+// result never aliases a later one while it is alive.
+namespace {
+struct PinnedPool {
+    std::mutex mu;
+    std::multimap<size_t, void *> free_;
+    size_t held = 0;
+    static constexpr size_t kMaxHeld = (size_t)1 << 30;
+    void *get(size_t cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            auto it = free_.find(cap);
+            if (it != free_.end()) {
+                void *p = it->second;
+                free_.erase(it);
+                held -= cap;
+                return p;
+            }
+        }
+        return fps_b200_host_alloc(cap);
+    }
+    void put(void *p, size_t cap) {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            if (held + cap <= kMaxHeld) {
+                free_.emplace(cap, p);
+                held += cap;
+                return;
+            }
+        }
+        fps_b200_host_free(p);
+    }
+};
+PinnedPool g_pool;
+struct PinnedBlock {
+    void *p;
+    size_t cap;
+};
+}  // namespace
+
+static py::array_t<size_t> index_array(size_t B, size_t k) {
+    const size_t bytes = B * k * sizeof(size_t);
+    if (bytes >= ((size_t)1 << 20)) {
+        const size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        if (void *p = g_pool.get(cap)) {
+            auto *blk = new PinnedBlock{p, cap};
+            py::capsule owner(blk, [](void *q) {
+                auto *b = static_cast<PinnedBlock *>(q);
+                g_pool.put(b->p, b->cap);
+                delete b;
+            });
+            return py::array_t<size_t>({(py::ssize_t)B, (py::ssize_t)k}, static_cast<size_t *>(p), owner);
+        }
+    }
+    return py::array_t<size_t>({(py::ssize_t)B, (py::ssize_t)k});
+}
+
 static std::vector<size_t> batch_starts(py::object start_obj, size_t B, size_t P) {
     std::vector<size_t> st;
     if (start_obj.is_none()) return st;
@@ -149,7 +210,7 @@ static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, s
     std::vector<size_t> st = batch_starts(start_obj, B, P);
     std::vector<int> devs;
     if (!devices_obj.is_none()) devs = devices_obj.cast<std::vector<int>>();
-    py::array_t<size_t> out({(py::ssize_t)B, (py::ssize_t)n_samples});
+    py::array_t<size_t> out = index_array(B, n_samples);
     int rc;
     {
         const float *src = points.data();
