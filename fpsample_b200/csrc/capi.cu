@@ -280,6 +280,14 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         // HBM-bound: BASELINE.json cfg 5) and a cloud would tie up 4 or more SMs
         prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp, ids) && tmp.flat && (ids || tmp.gc <= 2 || B < (size_t)4 * n_sms);
     }
+    if (build_only && plan_kdsmall(n, dim, h, B, n_sms, &L->sp)) {   // the build-only entry runs the kernel the samplers are fed by
+        L->small = true;
+        L->warp = false;
+        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        L->region_stride = kd_region_bytes(n, dim, h);
+        L->total = L->region_off + B * L->region_stride;
+        return cudaSuccess;
+    }
     L->warp = !build_only && !force_grid && !prefer_group && !ids && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
     if (L->warp) {
         L->async = false;
@@ -361,6 +369,16 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     a.dim = (u32)dim;
     a.k = (u32)k;
     a.h = (u32)h;
+    if (d_out == nullptr && L.small) {
+        unsigned char *region = static_cast<unsigned char *>(ws) + L.region_off;
+        set_plan("kdsmall_kernel<DIM=%d>(build only, %u CTAs per SM, smem=%zu) + kdsmall_export_kernel", L.sp.dimp, L.sp.occ, L.sp.smem);
+        tl_phase.mark(0, st);
+        CK(launch_kdsmall(L.sp, d_pts, region, L.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
+        CK(launch_kdsmall_export(region, L.region_stride, (u32)B, (u32)n, (u32)dim, (u32)h, perm_out, leaf_lo_out, leaf_box_out, st));
+        tl_phase.mark(1, st);
+        tl_phase.mark(2, st);
+        return FPS_OK;
+    }
     if (L.warp) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
@@ -566,12 +584,25 @@ static int run_shard(int dev, const ShardJob &j) {
                 CK(launch_kdsmall(sp, d_in + b0 * j.n * j.dim, region + b0 * L.region_stride, L.region_stride,
                                   reinterpret_cast<u32 *>(ws), (u32)nb, (u32)j.n, (u32)j.dim, (u32)j.h, ex.st));
             }
-            CK(launch_kdline_warp(L.wp, region, L.region_stride, d_starts, static_cast<u64 *>(cp.out.p),
+            // page-locked output (what the python module hands out): the sampler writes its 32-pick blocks straight into
+            // host memory over PCIe while it runs, no device-to-host copy afterwards
+            u64 *d_out = static_cast<u64 *>(cp.out.p);
+            bool zero_copy = false;
+            if (!getenv("FPS_B200_NO_ZEROCOPY")) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, j.out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
+                    d_out = static_cast<u64 *>(at.devicePointer);
+                    zero_copy = true;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+            CK(launch_kdline_warp(L.wp, region, L.region_stride, d_starts, d_out,
                                   reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
                                   ex.st));
-            CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
-            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + kdline_warp_kernel<DIM=%d,BPL=%u> clouds=%zu grid=%u",
-                     c, L.sp.dimp, L.wp.dimp, L.wp.bpl, j.B, L.wp.grid);
+            if (!zero_copy) CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
+            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + kdline_warp_kernel<DIM=%d,BPL=%u> clouds=%zu grid=%u%s",
+                     c, L.sp.dimp, L.wp.dimp, L.wp.bpl, j.B, L.wp.grid, zero_copy ? " + indices written straight to page-locked host memory" : "");
             for (auto &ln : cx->lane) {
                 cudaError_t e = cudaStreamSynchronize(ln.st);
                 if (e != cudaSuccess && rc == FPS_OK) {
@@ -880,7 +911,11 @@ size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t
         cudaGetLastError();
         return 0;
     }
-    return L.total;
+    size_t total = L.total;
+    KdLayout Lb;   // the build-only entry (fps_b200_kdline_build_dev) shares this query
+    if (kd_layout(B, n, dim, height, n_sms, true, &Lb) == cudaSuccess && Lb.total > total) total = Lb.total;
+    cudaGetLastError();
+    return total;
 }
 
 int fps_b200_vanilla_batch_dev(const float *d_points, size_t B, size_t n, size_t dim, size_t k,

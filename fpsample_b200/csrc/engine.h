@@ -84,6 +84,8 @@ bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPl
 // counter: 256 zero-able bytes of workspace (dynamic cloud scheduler)
 cudaError_t launch_kdsmall(const KdSmallPlan &pl, const float *pts, unsigned char *region, size_t region_stride,
                            u32 *counter, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
+cudaError_t launch_kdsmall_export(const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 dim, u32 h, u32 *perm_out,
+                                  u32 *leaf_lo_out, float *leaf_box_out, cudaStream_t st);
 
 // ---- kd-line, asynchronous coordinator/worker sampling over prebuilt regions (kdline_async.cu) -----------
 // per-cloud region: [q dim*npad f32][dis npad f32][perm npad u32][nlo pad32(S+1) u32][fbox S*2*dim f32]

@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(KS_T, 3) kdsmall_kernel(KdSmallArgs a, u32 *wo
                     for (int c = 0; c < DIM; ++c)
                         if (c < (int)dim) {
                             const float v = q[c * npad + i];
-                            mnL[c] = fminf(mnL[c], f ? v : PINF), mxL[c] = fmaxf(mxL[c], f ? v : NINF);
-                            mnR[c] = fminf(mnR[c], f ? PINF : v), mxR[c] = fmaxf(mxR[c], f ? NINF : v);
+                            if (f) mnL[c] = fminf(mnL[c], v), mxL[c] = fmaxf(mxL[c], v);   // predicated, no selects
+                            else mnR[c] = fminf(mnR[c], v), mxR[c] = fmaxf(mxR[c], v);
                         }
                 }
                 cnt = __reduce_add_sync(FULL, cnt);
@@ -330,6 +330,29 @@ __global__ void __launch_bounds__(KS_T, 3) kdsmall_kernel(KdSmallArgs a, u32 *wo
         for (u32 s = tid; s <= S; s += KS_T) r_nlo[s] = nlo[s];
         for (u32 e = tid; e < S * 2 * dim; e += KS_T) r_box[e] = ord2f(box[e]);
     }
+}
+
+// build-only entry (fps_b200_kdline_build_dev): copy permutation / slot boundaries / boxes out of the regions
+__global__ void kdsmall_export_kernel(const unsigned char *region, size_t region_stride, u32 n, u32 dim, u32 h, u32 *perm_out,
+                                      u32 *leaf_lo_out, float *leaf_box_out) {
+    const u32 cloud = blockIdx.x, S = 1u << h, npad = roundup32(n);
+    const unsigned char *rg = region + (size_t)cloud * region_stride;
+    const u32 *r_perm = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 1) * npad;
+    const u32 *r_nlo = r_perm + npad;
+    const float *r_box = reinterpret_cast<const float *>(r_nlo + ((S + 1 + 31) & ~31u));
+    if (perm_out)
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) perm_out[(size_t)cloud * n + i] = r_perm[i];
+    if (leaf_lo_out)
+        for (u32 s = threadIdx.x; s <= S; s += blockDim.x) leaf_lo_out[(size_t)cloud * (S + 1) + s] = r_nlo[s];
+    if (leaf_box_out)
+        for (u32 e = threadIdx.x; e < S * 2 * dim; e += blockDim.x) leaf_box_out[(size_t)cloud * S * 2 * dim + e] = r_box[e];
+}
+
+cudaError_t launch_kdsmall_export(const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 dim, u32 h, u32 *perm_out,
+                                  u32 *leaf_lo_out, float *leaf_box_out, cudaStream_t st) {
+    kdsmall_export_kernel<<<B, 256, 0, st>>>(region, region_stride, n, dim, h, perm_out, leaf_lo_out, leaf_box_out);
+    count_launch();
+    return cudaGetLastError();
 }
 
 // ======================================================================================================

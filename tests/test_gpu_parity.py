@@ -294,7 +294,11 @@ def test_unaligned_and_strided_inputs(oracle):
 def test_kdline_build_matches_oracle(oracle):
     """perm / leaf ranges / tight boxes of the GPU build == the oracle's."""
     import torch
-    for (n, d, h, gen) in [(4096, 3, 5, "u"), (20000, 3, 7, "l"), (3000, 6, 6, "g"), (100000, 3, 9, "u"), (64, 2, 6, "g")]:
+    # the small shapes go through kdsmall_kernel (the build behind the one-warp-per-cloud sampler): tie lattices in
+    # D = 1, 2, 3 make every misplaced permutation slot visible, which a tie-free cloud's indices would hide
+    for (n, d, h, gen) in [(4096, 3, 5, "u"), (20000, 3, 7, "l"), (3000, 6, 6, "g"), (100000, 3, 9, "u"), (64, 2, 6, "g"),
+                           (3000, 1, 6, "g"), (3000, 2, 6, "g"), (5000, 2, 7, "g"), (3000, 3, 6, "g"), (4099, 3, 5, "u"),
+                           (2000, 5, 4, "u"), (8000, 3, 7, "l"), (4096, 3, 8, "u")]:
         pc = {"u": lambda: synth.uniform(n, n, d), "l": lambda: synth.lidar(n, n),
               "g": lambda: synth.grid_ties(n, n, d)}[gen]()
         S = 1 << h
@@ -316,6 +320,20 @@ def test_kdline_build_matches_oracle(oracle):
         np.testing.assert_array_equal(glo[keep], obounds[:-1].astype(np.int64))
         assert glo[-1] == n
         np.testing.assert_array_equal(gbox[keep], obox)
+    # a batch: several clouds per CTA through the dynamic scheduler, shared memory reused from cloud to cloud
+    B, n, d, h = 500, 2500, 2, 6
+    pcs = np.stack([synth.grid_ties(900 + b, n, d, levels=5 + b % 7) for b in range(B)])
+    dp = torch.from_numpy(pcs).cuda()
+    perm = torch.empty((B, n), dtype=torch.int32, device="cuda")
+    wsb = capi.workspace_bytes(capi.ALGO_KDLINE, B, n, d, 1, h)
+    ws = torch.empty(wsb + 256, dtype=torch.uint8, device="cuda")
+    capi.kdline_build_dev(dp.data_ptr(), B, n, d, h, perm.data_ptr(), 0, 0, (ws.data_ptr() + 255) & ~255, wsb,
+                          torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert "kdsmall_kernel" in capi.last_plan(), capi.last_plan()
+    got = perm.cpu().numpy().astype(np.uint64)
+    for b in range(0, B, 7):
+        np.testing.assert_array_equal(got[b], oracle.kdline_build(pcs[b], h)[0], err_msg=f"cloud {b}")
 
 
 def test_device_pointer_entries(oracle):
