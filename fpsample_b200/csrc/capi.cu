@@ -283,7 +283,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     if (build_only && plan_kdsmall(n, dim, h, B, n_sms, &L->sp)) {   // the build-only entry runs the kernel the samplers are fed by
         L->small = true;
         L->warp = false;
-        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        L->region_off = ((L->pl.ws_bytes > L->sp.ws_bytes ? L->pl.ws_bytes : L->sp.ws_bytes) + 255) & ~(size_t)255;
         L->region_stride = kd_region_bytes(n, dim, h);
         L->total = L->region_off + B * L->region_stride;
         return cudaSuccess;
@@ -292,7 +292,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     if (L->warp) {
         L->async = false;
         L->small = plan_kdsmall(n, dim, h, B, n_sms, &L->sp);   // the build that feeds the regions
-        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        L->region_off = (((L->small && L->sp.ws_bytes > L->pl.ws_bytes) ? L->sp.ws_bytes : L->pl.ws_bytes) + 255) & ~(size_t)255;
         L->region_stride = kd_region_bytes(n, dim, h);
         L->counter_off = L->region_off + B * L->region_stride;
         L->total = L->counter_off + 256;
@@ -309,7 +309,11 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
         L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
         if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
-        L->region_off = (L->pl.ws_bytes + 255) & ~(size_t)255;
+        // a cloud whose coordinates fit one SM's shared memory is built by one CTA (kdsmall_kernel, 1024 threads): about
+        // 0.1 ms per wave of 148 clouds against 49 grid-wide launches (0.77 ms at BASELINE.json cfg 3)
+        L->small = !getenv("FPS_B200_GRIDBUILD") && plan_kdsmall(n, dim, h, B, n_sms, &L->sp);
+        if (L->small) L->gridbuild = false;
+        L->region_off = (((L->small && L->sp.ws_bytes > L->pl.ws_bytes) ? L->sp.ws_bytes : L->pl.ws_bytes) + 255) & ~(size_t)255;
         L->region_stride = kd_region_bytes(n, dim, h);
         L->aux_off = L->region_off + B * L->region_stride;
         L->total = L->aux_off + (L->gridbuild ? B * kd_gridbuild_aux_bytes(n, dim, h) : 0);
@@ -369,6 +373,23 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     a.dim = (u32)dim;
     a.k = (u32)k;
     a.h = (u32)h;
+    // the build that fills the per-cloud regions, by plan
+    auto build_regions = [&]() -> int {
+        if (L.small)
+            CK(launch_kdsmall(L.sp, d_pts, a.region, a.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
+        else if (L.gridbuild)
+            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
+                                   (u32)n, (u32)dim, (u32)h, st));
+        else
+            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        return FPS_OK;
+    };
+    char bdesc[128];
+    if (L.small)
+        snprintf(bdesc, sizeof bdesc, "kdsmall_kernel<DIM=%d,T=%d>(build in shared memory, %u CTA%s per SM, smem=%zu)", L.sp.dimp,
+                 L.sp.big ? 1024 : 256, L.sp.occ, L.sp.occ > 1 ? "s" : "", L.sp.smem);
+    else
+        snprintf(bdesc, sizeof bdesc, "%s", L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)");
     if (d_out == nullptr && L.small) {
         unsigned char *region = static_cast<unsigned char *>(ws) + L.region_off;
         set_plan("kdsmall_kernel<DIM=%d>(build only, %u CTAs per SM, smem=%zu) + kdsmall_export_kernel", L.sp.dimp, L.sp.occ, L.sp.smem);
@@ -382,20 +403,12 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     if (L.warp) {
         a.region = static_cast<unsigned char *>(ws) + L.region_off;
         a.region_stride = L.region_stride;
-        char bdesc[96];
-        if (L.small)
-            snprintf(bdesc, sizeof bdesc, "kdsmall_kernel<DIM=%d>(build in shared memory, %u CTAs per SM, smem=%zu)", L.sp.dimp, L.sp.occ, L.sp.smem);
-        else
-            snprintf(bdesc, sizeof bdesc, "kdline_kernel(build, 1 CTA per cloud)");
         set_plan("%s + kdline_warp%s_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
                  "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
                  bdesc, L.wp.global ? "g" : (L.wp.hybrid ? "(hybrid smem+tmem)" : ""), L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
                  L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
         tl_phase.mark(0, st);
-        if (L.small)
-            CK(launch_kdsmall(L.sp, d_pts, a.region, a.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
-        else
-            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
         CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
                               reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
@@ -410,13 +423,9 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         set_plan("%s%s + kdline_grid_kernel<DIM=%d,%s> clouds=%zu grid=%u (%u CTAs per cloud, %u clouds in flight) threads=1024 "
                  "points/thread=%u candidates/round<=%u smem=%zu region/cloud=%zu",
                  van_pts ? "vanilla FPS via kd permutation (ties by original index): " : "",
-                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.gp.dimp,
+                 bdesc, L.gp.dimp,
                  L.gp.flat ? "flat" : "merged", B, L.gp.G, L.gp.gc, L.gp.groups, L.gp.ppt, L.gp.ecap, L.gp.smem, L.region_stride);
-        if (L.gridbuild)
-            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
-                                   (u32)n, (u32)dim, (u32)h, st));
-        else
-            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
         a.starts = van_pts ? nullptr : d_starts;   // (the build kernels never read it)
         CK(launch_kdline_grid(L.gp, a.region, a.region_stride, d_starts, d_out, static_cast<unsigned char *>(ws) + L.pub_off,
@@ -432,13 +441,9 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         tl_phase.mark(0, st);
         set_plan("%s + kdline_dist_kernel<DIM=%d> clouds=%zu clusters=%u cluster=%u threads=%u buckets/CTA=%u "
                  "candidates/CTA=%u smem=%zu region/cloud=%zu",
-                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)",
+                 bdesc,
                  L.dp.dimp, B, L.dp.clusters, L.dp.C, L.dp.threads, L.dp.NB, L.dp.M, L.dp.smem, L.region_stride);
-        if (L.gridbuild)
-            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
-                                   (u32)n, (u32)dim, (u32)h, st));
-        else
-            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
         CK(launch_kdline_dist(L.dp, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h,
                               st));
@@ -451,13 +456,9 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         tl_phase.mark(0, st);
         set_plan("%s + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
                  "cluster=%u threads=%u smem=%zu R=%u region/cloud=%zu",
-                 L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)", L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
+                 bdesc, L.ap.dimp, B, L.ap.clusters, L.ap.C, L.ap.threads, L.ap.smem, L.ap.R,
                  L.region_stride);
-        if (L.gridbuild)
-            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
-                                   (u32)n, (u32)dim, (u32)h, st));
-        else
-            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+        if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
         CK(launch_kdline_async(L.ap, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k,
                                (u32)h, st));

@@ -77,13 +77,14 @@ cudaError_t launch_kdline(const KdlinePlan &pl, KdlineArgs a, unsigned char *ws_
 // ---- kd-line build for batches of small clouds, everything in one CTA's shared memory (kdsmall.cu) --------
 struct KdSmallPlan {
     int dimp;
-    u32 grid, occ;
+    u32 grid, occ, big;   // big: 1024 threads, one CTA per SM, index arrays in global memory
     size_t smem;
+    size_t ws_bytes;      // 256-byte scheduler counter + the big variant's index arrays
 };
 bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPlan *pl);
-// counter: 256 zero-able bytes of workspace (dynamic cloud scheduler)
+// ws: pl.ws_bytes of workspace (dynamic cloud scheduler counter, then the big variant's index arrays)
 cudaError_t launch_kdsmall(const KdSmallPlan &pl, const float *pts, unsigned char *region, size_t region_stride,
-                           u32 *counter, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
+                           u32 *ws, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st);
 cudaError_t launch_kdsmall_export(const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 dim, u32 h, u32 *perm_out,
                                   u32 *leaf_lo_out, float *leaf_box_out, cudaStream_t st);
 

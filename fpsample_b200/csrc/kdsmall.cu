@@ -26,12 +26,11 @@
 
 namespace fps {
 
-constexpr u32 KS_T = 256, KS_NW = KS_T / 32;
-
 struct KdSmallArgs {
     const float *pts;        // [B][n][dim]
     unsigned char *region;   // per cloud: [q dim*npad f32][dis npad f32][perm npad u32][nlo pad32(S+1) u32][fbox S*2*dim f32]
     size_t region_stride;
+    unsigned short *idx_ws;  // IDXG: per resident CTA, permutation + misplaced-position scratch (2 * npad u16) in global memory
     u32 B, n, dim, h;
 };
 
@@ -94,8 +93,12 @@ __device__ __forceinline__ void ks_box_write(const float *q, u32 npad, u32 dim, 
         }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(KS_T, 3) kdsmall_kernel(KdSmallArgs a, u32 *work_counter) {
+// T threads per CTA: 256 with three CTAs per SM for clouds of a few thousand points, 1024 with one CTA per SM for clouds
+// whose coordinates alone fill the SM's shared memory (16 384 x 3: BASELINE.json cfg 3); IDXG moves the two 16-bit index
+// arrays of such a cloud to global memory (L2-resident, touched only by the scatter / swap phases).
+template <int DIM, int T, bool IDXG>
+__global__ void __launch_bounds__(T, T == 256 ? 3 : 1) kdsmall_kernel(KdSmallArgs a, u32 *work_counter) {
+    constexpr u32 KS_T = T, KS_NW = T / 32;
     extern __shared__ __align__(16) unsigned char ks_smem[];
     __shared__ u32 cloud_s;
     const u32 tid = threadIdx.x, lane = lane_id(), warp = warp_id();
@@ -105,9 +108,17 @@ __global__ void __launch_bounds__(KS_T, 3) kdsmall_kernel(KdSmallArgs a, u32 *wo
     const u32 PN = S > KS_NW ? S : KS_NW;                // (node, rank) pairs: j * ts + rank < NW on the block-synchronous levels
 
     float *q = reinterpret_cast<float *>(ks_smem);                       // [dim][npad] SoA, permuted in place
-    unsigned short *pm = reinterpret_cast<unsigned short *>(q + (size_t)dim * npad);   // [npad] position -> original id
-    unsigned short *scr = pm + npad;                                     // [npad] misplaced positions of the level
-    u32 *nlo = reinterpret_cast<u32 *>(scr + npad);                      // [S + 1] slot boundaries
+    unsigned short *pm, *scr;   // [npad] position -> original id; [npad] misplaced positions of the level
+    u32 *nlo;                   // [S + 1] slot boundaries
+    if constexpr (IDXG) {
+        pm = a.idx_ws + (size_t)blockIdx.x * 2 * npad;
+        scr = pm + npad;
+        nlo = reinterpret_cast<u32 *>(q + (size_t)dim * npad);
+    } else {
+        pm = reinterpret_cast<unsigned short *>(q + (size_t)dim * npad);
+        scr = pm + npad;
+        nlo = reinterpret_cast<u32 *>(scr + npad);
+    }
     int *box = reinterpret_cast<int *>(nlo + S + 1);                     // [S][2][dim] ordered ints
     u32 *nval = reinterpret_cast<u32 *>(box + (size_t)S * 2 * dim);      // [S] split value bits, by heap number
     u32 *nsd = nval + S;                                                 // [S] split dim
@@ -360,36 +371,47 @@ cudaError_t launch_kdsmall_export(const unsigned char *region, size_t region_str
 // ======================================================================================================
 static int ks_pad_dim(int dim) { return dim <= 2 ? 2 : dim == 3 ? 3 : dim == 4 ? 4 : dim <= 6 ? 6 : 8; }
 
-static size_t ks_smem_bytes(size_t n, size_t dim, size_t h) {
+static size_t ks_smem_bytes(size_t n, size_t dim, size_t h, bool idxg, size_t nw) {
     const size_t S = (size_t)1 << h, npad = (n + 31) & ~(size_t)31;
-    const size_t PN = S > KS_NW ? S : KS_NW;
-    return dim * npad * 4 + 2 * npad * 2 + ((S + 1) + S * 2 * dim + 3 * S + 2 * PN) * 4 + 16;
+    const size_t PN = S > nw ? S : nw;
+    return dim * npad * 4 + (idxg ? 0 : 2 * npad * 2) + ((S + 1) + S * 2 * dim + 3 * S + 2 * PN) * 4 + 16;
+}
+
+template <int DIM, int T, bool IDXG>
+static cudaError_t ks_occupancy(size_t smem, int *occ) {
+    auto kern = kdsmall_kernel<DIM, T, IDXG>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, T, smem);
 }
 
 template <int DIM>
-static cudaError_t ks_occupancy(size_t smem, int *occ) {
-    auto kern = kdsmall_kernel<DIM>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, (int)KS_T, smem);
+static cudaError_t ks_occupancy_d(bool big, size_t smem, int *occ) {
+    return big ? ks_occupancy<DIM, 1024, true>(smem, occ) : ks_occupancy<DIM, 256, false>(smem, occ);
 }
 
 bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPlan *pl) {
     if (dim == 0 || dim > 8 || n == 0 || n > 65535 || h == 0 || h > 8 || B == 0) return false;
     if (const char *e = getenv("FPS_B200_KDSMALL"))
         if (atoi(e) == 0) return false;
-    const size_t smem = ks_smem_bytes(n, dim, h);
-    if (smem > 110 * 1024) return false;   // at least two clouds in flight per SM, or the general kernel does as well
+    size_t smem = ks_smem_bytes(n, dim, h, false, 8);
+    bool big = false;
+    if (smem > 110 * 1024) {   // fewer than two clouds per SM: one CTA of 1024 threads per SM, index arrays in global memory
+        big = true;
+        smem = ks_smem_bytes(n, dim, h, true, 32);
+        if (smem > 225 * 1024) return false;
+    }
     pl->dimp = ks_pad_dim((int)dim);
     pl->smem = smem;
+    pl->big = big ? 1 : 0;
     int occ = 0;
     cudaError_t e;
     switch (pl->dimp) {
-        case 2: e = ks_occupancy<2>(smem, &occ); break;
-        case 3: e = ks_occupancy<3>(smem, &occ); break;
-        case 4: e = ks_occupancy<4>(smem, &occ); break;
-        case 6: e = ks_occupancy<6>(smem, &occ); break;
-        default: e = ks_occupancy<8>(smem, &occ); break;
+        case 2: e = ks_occupancy_d<2>(big, smem, &occ); break;
+        case 3: e = ks_occupancy_d<3>(big, smem, &occ); break;
+        case 4: e = ks_occupancy_d<4>(big, smem, &occ); break;
+        case 6: e = ks_occupancy_d<6>(big, smem, &occ); break;
+        default: e = ks_occupancy_d<8>(big, smem, &occ); break;
     }
     if (e != cudaSuccess || occ < 1) {
         cudaGetLastError();
@@ -399,24 +421,34 @@ bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPl
     if (grid > B) grid = B;
     pl->grid = (u32)grid;
     pl->occ = (u32)occ;
+    const size_t npad = (n + 31) & ~(size_t)31;
+    pl->ws_bytes = 256 + (big ? (size_t)occ * (size_t)n_sms * 2 * npad * sizeof(unsigned short) : 0);
     return true;
 }
 
+template <int DIM>
+static void ks_launch_d(const KdSmallPlan &pl, const KdSmallArgs &a, u32 *counter, cudaStream_t st) {
+    if (pl.big) kdsmall_kernel<DIM, 1024, true><<<pl.grid, 1024, pl.smem, st>>>(a, counter);
+    else kdsmall_kernel<DIM, 256, false><<<pl.grid, 256, pl.smem, st>>>(a, counter);
+}
+
+// ws: pl.ws_bytes of workspace (256 bytes of scheduler counter, then the index arrays of the big variant)
 cudaError_t launch_kdsmall(const KdSmallPlan &pl, const float *pts, unsigned char *region, size_t region_stride,
-                           u32 *counter, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st) {
-    cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
+                           u32 *ws, u32 B, u32 n, u32 dim, u32 h, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(ws, 0, 256, st);
     if (e != cudaSuccess) return e;
     KdSmallArgs a;
     a.pts = pts;
     a.region = region;
     a.region_stride = region_stride;
+    a.idx_ws = reinterpret_cast<unsigned short *>(reinterpret_cast<unsigned char *>(ws) + 256);
     a.B = B, a.n = n, a.dim = dim, a.h = h;
     switch (pl.dimp) {
-        case 2: kdsmall_kernel<2><<<pl.grid, KS_T, pl.smem, st>>>(a, counter); break;
-        case 3: kdsmall_kernel<3><<<pl.grid, KS_T, pl.smem, st>>>(a, counter); break;
-        case 4: kdsmall_kernel<4><<<pl.grid, KS_T, pl.smem, st>>>(a, counter); break;
-        case 6: kdsmall_kernel<6><<<pl.grid, KS_T, pl.smem, st>>>(a, counter); break;
-        default: kdsmall_kernel<8><<<pl.grid, KS_T, pl.smem, st>>>(a, counter); break;
+        case 2: ks_launch_d<2>(pl, a, ws, st); break;
+        case 3: ks_launch_d<3>(pl, a, ws, st); break;
+        case 4: ks_launch_d<4>(pl, a, ws, st); break;
+        case 6: ks_launch_d<6>(pl, a, ws, st); break;
+        default: ks_launch_d<8>(pl, a, ws, st); break;
     }
     count_launch();
     return cudaGetLastError();

@@ -298,7 +298,9 @@ def test_kdline_build_matches_oracle(oracle):
     # D = 1, 2, 3 make every misplaced permutation slot visible, which a tie-free cloud's indices would hide
     for (n, d, h, gen) in [(4096, 3, 5, "u"), (20000, 3, 7, "l"), (3000, 6, 6, "g"), (100000, 3, 9, "u"), (64, 2, 6, "g"),
                            (3000, 1, 6, "g"), (3000, 2, 6, "g"), (5000, 2, 7, "g"), (3000, 3, 6, "g"), (4099, 3, 5, "u"),
-                           (2000, 5, 4, "u"), (8000, 3, 7, "l"), (4096, 3, 8, "u")]:
+                           (2000, 5, 4, "u"), (8000, 3, 7, "l"), (4096, 3, 8, "u"),
+                           # one CTA of 1024 threads per cloud, index arrays in global memory (cfg 3's shape)
+                           (16384, 3, 7, "u"), (16000, 2, 7, "g"), (12000, 4, 6, "u"), (17000, 3, 8, "g")]:
         pc = {"u": lambda: synth.uniform(n, n, d), "l": lambda: synth.lidar(n, n),
               "g": lambda: synth.grid_ties(n, n, d)}[gen]()
         S = 1 << h
