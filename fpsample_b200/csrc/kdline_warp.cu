@@ -68,7 +68,7 @@ __device__ __forceinline__ void sts64(u32 a, float x, float y) {
 // ---- the two point stores ---------------------------------------------------------------------------------------
 // component c (0..DIM-1 coordinates, DIM = running distance) of position (chunk, lane)
 struct SmemStore {
-    static constexpr bool kTrackCoords = false;
+    static constexpr bool kTrackCoords = false, kCoordsInPlace = false;
     u32 base;   // shared-space byte address of this warp's slot
     u32 lst;    // words per (component, lane) row: nch + 4 (16-byte aligned rows, conflict-free 128-bit access)
     __device__ __forceinline__ u32 addr(u32 comp, u32 lane, u32 chunk) const { return base + ((comp * 32u + lane) * lst + chunk) * 4u; }
@@ -109,7 +109,9 @@ struct SmemStore {
 };
 
 struct TmemStore {
-    static constexpr bool kTrackCoords = false;
+    // a point lookup is three tcgen05.ld + a wait + three shuffles on the pick path: lanes remember their candidate's
+    // coordinates instead (three selects per chunk of a bucket pass) and the winner broadcasts them
+    static constexpr bool kTrackCoords = true, kCoordsInPlace = false;
     u32 base;   // tensor-memory address of this warp's lane quarter: (32 * (warp % 4)) << 16 | first column
     u32 nch;    // columns per component
     __device__ __forceinline__ void ld4(u32 col, u32 *w) const {
@@ -172,7 +174,7 @@ struct TmemStore {
 // (BASELINE.json cfg 3) is 192 KB of coordinates + 64 KB of distances -- more than either store alone, exactly what one
 // SM has when both are used.  One such warp per SM (its distances fill one lane quarter of TMEM).
 struct HybridStore {
-    static constexpr bool kTrackCoords = false;
+    static constexpr bool kTrackCoords = false, kCoordsInPlace = false;
     SmemStore s;   // DIM components
     TmemStore t;   // one component: the distance of chunk c is column c
     u32 dimc;      // index of the distance component (= DIM of the kernel)
@@ -199,6 +201,7 @@ struct HybridStore {
 // bytes per point-update.  A warp access is 32 consecutive positions = one 128-byte line per component.
 struct GlobalStore {
     static constexpr bool kTrackCoords = true;   // a point lookup would be an L2 / HBM round trip on the pick path
+    static constexpr bool kCoordsInPlace = true; // the region already holds the coordinates: only distances are staged
     const float *q;   // [dim][npad]
     float *dis;       // [npad]
     u32 npad, n;
@@ -262,7 +265,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
     // ---- stage the permuted cloud into this warp's store; distances start at FLT_MAX (Point.h:61-65) ---------
     for (u32 cb = 0; cb < nch; cb += W_U) {
 #pragma unroll
-        for (int c = ST::kTrackCoords ? DIM : 0; c <= DIM; ++c) {   // a global store holds the coordinates already
+        for (int c = ST::kCoordsInPlace ? DIM : 0; c <= DIM; ++c) {   // a global store holds the coordinates already
             float v[W_U];
 #pragma unroll
             for (int u = 0; u < W_U; ++u) {
@@ -304,6 +307,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
 #pragma unroll
     for (int c = 0; c < DIM; ++c) r[c] = (c < (int)dim) ? __ldg(q + (size_t)c * npad + cur) : 0.0f;
     u32 mypos = cur;   // lane (t % 32) remembers pick t until the block of 32 picks is written out
+    u32 idv = 0;       // ids of the block being written out
 
 #if WDBG
     u64 dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -372,15 +376,18 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
 #if WDBG
                 dbg[6] += nref;
 #endif
+                // the next pending sample is fetched while the current one is applied
+                const u32 e0 = pend + b * PRB, estep = S * PRB;
+                float4 n0 = lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if constexpr (DIM > 4) n1 = lds128(e0 + 16u);
                 for (u32 i = 0; i < nref; ++i) {
-                    const u32 e = pend + (i * S + b) * PRB;
+                    const float4 f0 = n0, f1 = n1;
+                    const u32 en = e0 + min(i + 1, nref - 1) * estep;
+                    n0 = lds128(en);
+                    if constexpr (DIM > 4) n1 = lds128(en + 16u);
                     float w[8];
-                    const float4 f0 = lds128(e);
                     w[0] = f0.x, w[1] = f0.y, w[2] = f0.z, w[3] = f0.w;
-                    if constexpr (DIM > 4) {
-                        const float4 f1 = lds128(e + 16u);
-                        w[4] = f1.x, w[5] = f1.y, w[6] = f1.z, w[7] = f1.w;
-                    }
+                    if constexpr (DIM > 4) w[4] = f1.x, w[5] = f1.y, w[6] = f1.z, w[7] = f1.w;
                     float ref[DIM];
 #pragma unroll
                     for (int c = 0; c < DIM; ++c) ref[c] = w[c];
@@ -478,9 +485,10 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             st.load_point(cur, lane, r);
         }
         // ---- output: positions are turned into original ids 32 picks at a time (wrapper.hpp:57-59) -----------------
-        if ((t & 31u) == 0) {
-            out[t - 32 + lane] = (u64)__ldg(perm + mypos);
-        }
+        // the id lookup of a finished block is issued one pick before its result is stored: its L2 latency hides
+        // behind that pick's work
+        if ((t & 31u) == 0) idv = __ldg(perm + mypos);
+        if ((t & 31u) == 1 && t > 1) out[t - 33 + lane] = (u64)idv;
         if (lane == (t & 31u)) mypos = cur;
 #if WDBG
         const long long c3 = clock64();
@@ -495,6 +503,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
     if (cloud == 0 && lane == 0)
         for (int i = 0; i < 8; ++i) g_warp_dbg[i] = dbg[i];
 #endif
+    if (k > 32 && ((k - 1) & 31u) == 0) out[k - 33 + lane] = (u64)idv;   // the block whose lookup the last pick issued
     {   // tail: picks [k0, k)
         const u32 k0 = (k - 1) & ~31u;
         if (k0 + lane < k) out[k0 + lane] = (u64)__ldg(perm + mypos);

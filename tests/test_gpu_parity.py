@@ -338,6 +338,17 @@ def test_kdline_build_matches_oracle(oracle):
         np.testing.assert_array_equal(got[b], oracle.kdline_build(pcs[b], h)[0], err_msg=f"cloud {b}")
 
 
+def test_kdline_pick_counts_around_output_blocks(oracle):
+    """the one-warp-per-cloud sampler writes ids in blocks of 32 picks, one pick late: every residue of k matters"""
+    pc = synth.uniform(321, 4096, 3)
+    pcs = synth.uniform_batch(322, 9, 3000, 3)
+    for k in (1, 2, 31, 32, 33, 34, 63, 64, 65, 97, 993, 1025):
+        np.testing.assert_array_equal(capi.kdline(pc, k, 5, 7), oracle.kdline(pc, k, 5, 7), err_msg=f"k={k}")
+        got = capi.kdline_batch(pcs, k, 4, None, devices=[0])
+        for b in range(9):
+            np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, 4, 0), err_msg=f"k={k} cloud {b}")
+
+
 def test_device_pointer_entries(oracle):
     import torch
     B, n, d, k, h = 6, 5000, 3, 400, 5
