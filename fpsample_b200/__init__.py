@@ -26,6 +26,7 @@ try:
         _bucket_fps_kdline_sampling_batch,
         _bucket_fps_kdtree_sampling,
         _bucket_fps_kdtree_sampling_batch,
+        _batch_ptr,
         _device_count,
         _fps_sampling,
         _fps_sampling_batch,
@@ -36,6 +37,47 @@ except ImportError as e:  # pragma: no cover - build problem, never a silent fal
     raise ImportError(
         "fpsample_b200: the native CUDA extension is not built (run `python build_native.py`); "
         "there is no CPU fallback") from e
+
+
+_VANILLA, _KDLINE, _KDTREE = 0, 1, 2
+
+
+def _cuda_view(a, ndim: int):
+    """(address, shape) of a GPU-resident array (anything with __cuda_array_interface__: torch, cupy, numba), else None.
+
+    SURVEY.md 8(f) row 3: clouds that are already in HBM are sampled where they are.  No implicit casts or copies on
+    the device: the buffer has to be C-contiguous float32; work that produces it must be enqueued before the call (the
+    library synchronises the device before reading it).  The index array still comes back as a host numpy array.
+    """
+    cai = getattr(a, "__cuda_array_interface__", None)
+    if cai is None:
+        return None
+    shape = tuple(int(x) for x in cai["shape"])
+    if len(shape) != ndim:
+        raise ValueError(f"expected a {ndim}-D device array, got shape {shape}")
+    if cai["typestr"] not in ("<f4", "=f4", "|f4"):
+        raise TypeError("device arrays must be float32 (cast on the device before the call)")
+    strides = cai.get("strides")
+    if strides is not None:
+        want, acc = [], 4
+        for dim in reversed(shape):
+            want.append(acc)
+            acc *= dim
+        if tuple(strides) != tuple(reversed(want)):
+            raise TypeError("device arrays must be C-contiguous")
+    return int(cai["data"][0]), shape
+
+
+def _device_single(algo: int, dv, n_samples: int, h: int, start_idx):
+    ptr, (n_pts, d) = dv
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    if start_idx is None:
+        start_idx = int(np.random.randint(low=0, high=n_pts))
+    if not isinstance(start_idx, int):
+        raise TypeError("a device array takes start_idx None or int")
+    assert 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    return _batch_ptr(algo, ptr, 1, n_pts, d, n_samples, h, start_idx, None)[0]
 
 
 def get_start_idx(n_pts: int, start_idx: Optional[Union[int, List[int]]]) -> Union[int, np.ndarray]:
@@ -62,6 +104,9 @@ def fps_sampling(pc: np.ndarray, n_samples: int,
     Returns:
         uint64 indices of shape (n_samples,).
     """
+    dv = _cuda_view(pc, 2)
+    if dv is not None:
+        return _device_single(_VANILLA, dv, n_samples, 0, start_idx)
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pc.ndim == 2
     n_pts, _ = pc.shape
@@ -84,6 +129,11 @@ def bucket_fps_kdline_sampling(pc: np.ndarray, n_samples: int, h: int,
     As in the reference, start_idx addresses the POSITION in the array after the kd build permuted it
     (src/wrapper.hpp:54-55), so out[0] is generally not start_idx.
     """
+    dv = _cuda_view(pc, 2)
+    if dv is not None:
+        assert h >= 1, "h should be >= 1"
+        assert 2**h <= dv[1][0], "2**h should be <= n_pts"
+        return _device_single(_KDLINE, dv, n_samples, h, start_idx)
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pc.ndim == 2
     n_pts, _ = pc.shape
@@ -105,6 +155,9 @@ def bucket_fps_kdtree_sampling(pc: np.ndarray, n_samples: int,
     As in the reference, start_idx addresses the POSITION in the array after the (full-depth) kd build permuted
     it (src/wrapper.hpp:36-37), and distance ties go to the highest position (src/_ext/KDNode.h:41-46).
     """
+    dv = _cuda_view(pc, 2)
+    if dv is not None:
+        return _device_single(_KDTREE, dv, n_samples, 0, start_idx)
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pc.ndim == 2
     n_pts, _ = pc.shape
@@ -135,6 +188,13 @@ def fps_sampling_batch(pcs: np.ndarray, n_samples: int,
     start_idx None means 0 for every cloud (a batch is deterministic by default).  The batch is split
     into contiguous shards over `devices` (default: every visible B200); no inter-GPU traffic.
     """
+    dv = _cuda_view(pcs, 3)
+    if dv is not None:   # GPU-resident batch: sampled where it lives
+        ptr, (b, n_pts, d) = dv
+        assert n_samples >= 1, "n_samples should be >= 1"
+        assert n_pts >= n_samples, "n_pts should be >= n_samples"
+        return _batch_ptr(_VANILLA, ptr, b, n_pts, d, n_samples, 0, _batch_start(start_idx, b, n_pts),
+                          None if devices is None else list(devices))
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pcs.ndim == 3
     b, n_pts, _ = pcs.shape
@@ -148,6 +208,15 @@ def bucket_fps_kdline_sampling_batch(pcs: np.ndarray, n_samples: int, h: int,
                                      start_idx: Optional[Union[int, Sequence[int]]] = None,
                                      devices: Optional[Sequence[int]] = None) -> np.ndarray:
     """QuickFPS kd-line over a batch [B, N, D]; row b equals bucket_fps_kdline_sampling(pcs[b], ...)."""
+    dv = _cuda_view(pcs, 3)
+    if dv is not None:   # GPU-resident batch: sampled where it lives
+        ptr, (b, n_pts, d) = dv
+        assert n_samples >= 1, "n_samples should be >= 1"
+        assert n_pts >= n_samples, "n_pts should be >= n_samples"
+        assert h >= 1, "h should be >= 1"
+        assert 2**h <= n_pts, "2**h should be <= n_pts"
+        return _batch_ptr(_KDLINE, ptr, b, n_pts, d, n_samples, h, _batch_start(start_idx, b, n_pts),
+                          None if devices is None else list(devices))
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pcs.ndim == 3
     b, n_pts, _ = pcs.shape
@@ -163,6 +232,13 @@ def bucket_fps_kdtree_sampling_batch(pcs: np.ndarray, n_samples: int,
                                      start_idx: Optional[Union[int, Sequence[int]]] = None,
                                      devices: Optional[Sequence[int]] = None) -> np.ndarray:
     """QuickFPS full kd tree over a batch [B, N, D]; row b equals bucket_fps_kdtree_sampling(pcs[b], ...)."""
+    dv = _cuda_view(pcs, 3)
+    if dv is not None:   # GPU-resident batch: sampled where it lives
+        ptr, (b, n_pts, d) = dv
+        assert n_samples >= 1, "n_samples should be >= 1"
+        assert n_pts >= n_samples, "n_pts should be >= n_samples"
+        return _batch_ptr(_KDTREE, ptr, b, n_pts, d, n_samples, 0, _batch_start(start_idx, b, n_pts),
+                          None if devices is None else list(devices))
     assert n_samples >= 1, "n_samples should be >= 1"
     assert pcs.ndim == 3
     b, n_pts, _ = pcs.shape

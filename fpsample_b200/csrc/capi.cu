@@ -538,6 +538,21 @@ static int run_shard(int dev, const ShardJob &j) {
         cx->ready = true;
     }
     const size_t in_per = j.n * j.dim * sizeof(float), out_per = j.k * sizeof(u64);
+    // input already in this device's memory (a pointer from cudaMalloc, torch, cupy ...): no upload, the kernels read it
+    bool dev_in = false;
+    {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, j.pts) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            if (at.device != dev) {
+                set_err("points live on device %d but the shard runs on device %d", at.device, dev);
+                return FPS_ERR_ARG;
+            }
+            dev_in = true;
+            CK(cudaDeviceSynchronize());   // whatever produced the buffer (on any stream of the caller) has finished
+        } else {
+            cudaGetLastError();
+        }
+    }
     // chunks overlap the upload of one with the kernels of the other (two lanes); each chunk must still be a batch the
     // samplers like: >= 1024 clouds (the one-warp-per-cloud kernels want every SM stacked) and >= 32 MB of input
     size_t nch = 1;
@@ -546,6 +561,7 @@ static int run_shard(int dev, const ShardJob &j) {
         nch = by_bytes < by_clouds ? by_bytes : by_clouds;
         if (nch < 1) nch = 1;
         if (nch > 8) nch = 8;
+        if (dev_in) nch = 1;
     }
     const size_t chunk = (j.B + nch - 1) / nch;
     static_assert(sizeof(size_t) == sizeof(u64), "size_t must be 64-bit");
@@ -553,7 +569,7 @@ static int run_shard(int dev, const ShardJob &j) {
     // One batch of small clouds (the on-chip sampler wants all of them in one launch): the upload is cut into pieces and
     // every piece is BUILT (kdsmall_kernel, into its clouds' regions) while the next one is still crossing PCIe; the
     // sampler then runs once over the whole batch.  Copy engine on lane 0's stream, kernels on lane 1's.
-    if (j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && !getenv("FPS_B200_NO_PIPE")) {
+    if (!dev_in && j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && !getenv("FPS_B200_NO_PIPE")) {
         KdLayout L;
         CK(kd_layout(j.B, j.n, j.dim, j.h, cx->n_sms, false, &L));
         if (L.warp && L.small) {
@@ -631,7 +647,8 @@ static int run_shard(int dev, const ShardJob &j) {
             CK(kd_layout(nb, j.n, j.dim, j.h, cx->n_sms, false, &L));
             ws_need = L.total;
         }
-        if ((rc = ln.in.ensure(nb * in_per)) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) break;
+        if ((!dev_in && (rc = ln.in.ensure(nb * in_per))) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) break;
+        const float *d_in = dev_in ? j.pts + b0 * j.n * j.dim : static_cast<const float *>(ln.in.p);
         u64 *d_starts = nullptr;
         if (j.start) {
             if ((rc = ln.starts.ensure(nb * j.n_starts * sizeof(u64)))) break;
@@ -639,15 +656,15 @@ static int run_shard(int dev, const ShardJob &j) {
             CK(cudaMemcpyAsync(d_starts, j.start + b0 * j.n_starts, nb * j.n_starts * sizeof(u64),
                                cudaMemcpyHostToDevice, ln.st));
         }
-        CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
+        if (!dev_in) CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
         if (j.algo == FPS_ALGO_VANILLA)
-            rc = enqueue_vanilla(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.n_starts,
+            rc = enqueue_vanilla(d_in, nb, j.n, j.dim, j.k, d_starts, j.n_starts,
                                  static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else if (j.algo == FPS_ALGO_KDTREE)
-            rc = enqueue_kdtree(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts,
+            rc = enqueue_kdtree(d_in, nb, j.n, j.dim, j.k, d_starts,
                                 static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else
-            rc = enqueue_kdline(static_cast<const float *>(ln.in.p), nb, j.n, j.dim, j.k, d_starts, j.h,
+            rc = enqueue_kdline(d_in, nb, j.n, j.dim, j.k, d_starts, j.h,
                                 static_cast<u64 *>(ln.out.p), nullptr, nullptr, nullptr, ln.ws.p, ln.ws.cap,
                                 cx->n_sms, ln.st);
         if (rc) break;
@@ -679,6 +696,19 @@ static int run_batch(ShardJob j, const int *devices, int n_devices) {
             set_err("device %d is not a usable sm_100 device", d);
             return FPS_ERR_NO_DEVICE;
         }
+    {   // a device-resident batch is sampled where it lives
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, j.pts) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+            bool listed = !(devices && n_devices > 0);
+            for (int d : devs) listed = listed || d == at.device;
+            if (!listed || !get_ctx(at.device)) {
+                set_err("points live on device %d, which is not among the requested / usable devices", at.device);
+                return FPS_ERR_ARG;
+            }
+            return run_shard(at.device, j);
+        }
+        cudaGetLastError();
+    }
     size_t G = devs.size();
     if (G > j.B) G = j.B;
     if (G == 1) return run_shard(devs[0], j);

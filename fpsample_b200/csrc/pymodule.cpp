@@ -199,10 +199,8 @@ static std::vector<size_t> batch_starts(py::object start_obj, size_t B, size_t P
     return st;
 }
 
-static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, size_t height, py::object start_obj,
-                                    py::object devices_obj) {
-    if (points.ndim() != 3) throw py::value_error("points must be a 3D array [B, N, D]");
-    const size_t B = (size_t)points.shape(0), P = (size_t)points.shape(1), C = (size_t)points.shape(2);
+static py::array_t<size_t> batch_core(int algo, const float *src, size_t B, size_t P, size_t C, size_t n_samples, size_t height,
+                                      py::object start_obj, py::object devices_obj) {
     if (B == 0) throw py::value_error("batch must hold at least one cloud");
     if (C == 0) throw py::value_error("points must have at least one column");
     if (n_samples == 0 || n_samples > P) throw py::value_error("n_samples must be in [1, num_points]");
@@ -213,7 +211,6 @@ static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, s
     py::array_t<size_t> out = index_array(B, n_samples);
     int rc;
     {
-        const float *src = points.data();
         size_t *dst = out.mutable_data();
         const size_t *sp = st.empty() ? nullptr : st.data();
         const int *dp = devs.empty() ? nullptr : devs.data();
@@ -228,6 +225,21 @@ static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, s
     if (rc != 0)
         raise_rc(algo == FPS_ALGO_VANILLA ? "fps_b200_vanilla_batch" : algo == FPS_ALGO_KDTREE ? "fps_b200_kdtree_batch" : "fps_b200_kdline_batch", rc);
     return out;
+}
+
+static py::array_t<size_t> batch_py(int algo, farray points, size_t n_samples, size_t height, py::object start_obj,
+                                    py::object devices_obj) {
+    if (points.ndim() != 3) throw py::value_error("points must be a 3D array [B, N, D]");
+    return batch_core(algo, points.data(), (size_t)points.shape(0), (size_t)points.shape(1), (size_t)points.shape(2), n_samples,
+                      height, start_obj, devices_obj);
+}
+
+// the same over a raw address: a C-contiguous float32 [B, N, D] buffer that already lives in GPU memory (torch / cupy /
+// numba arrays through __cuda_array_interface__); the library samples it where it is, no upload
+static py::array_t<size_t> batch_ptr_py(int algo, size_t address, size_t B, size_t P, size_t C, size_t n_samples, size_t height,
+                                        py::object start_obj, py::object devices_obj) {
+    if (address == 0) throw py::value_error("null device pointer");
+    return batch_core(algo, reinterpret_cast<const float *>(address), B, P, C, n_samples, height, start_obj, devices_obj);
 }
 
 PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
@@ -247,6 +259,8 @@ PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
     m.def("_bucket_fps_kdline_sampling_batch",
           [](farray p, size_t k, size_t h, py::object s, py::object d) { return batch_py(FPS_ALGO_KDLINE, p, k, h, s, d); },
           "Batched QuickFPS kd-line. points: B x N x C; height; start_idx: None|int|int[B]; devices: None|list[int].");
+    m.def("_batch_ptr", &batch_ptr_py,
+          "Batched entry over a raw float32 [B, N, D] address (device memory): algo 0 vanilla / 1 kd-line / 2 kd tree.");
     m.def("_device_count", []() { return fps_b200_device_count(); });
     m.def("_last_plan", []() { return std::string(fps_b200_last_plan()); });
     m.def("_kernel_launches", []() { return fps_b200_kernel_launches(); });

@@ -12,7 +12,9 @@
  *   - indices out are size_t / uint64 (src/lib.cpp:240-245, 561-562), [k] or [B][k].
  *   - return 0 on success.  1 and 2 keep the reference's meaning (src/wrapper.hpp:121-127).
  *   - host-pointer entry points are synchronous and re-entrant; device memory, streams and
- *     workspaces are private to the library.  *_dev entry points take device pointers and a CUDA
+ *     workspaces are private to the library.  `points` may also be a DEVICE pointer (the clouds are then
+ *     sampled on the device they live on, without an upload, after a device synchronise); page-locked
+ *     buffers make the host path faster (pipelined upload, indices written straight into `out`).  *_dev entry points take device pointers and a CUDA
  *     stream (void* == cudaStream_t) and only enqueue work.
  *   - there is NO CPU fallback: without a usable sm_100 device the calls fail with FPS_ERR_NO_DEVICE.
  */

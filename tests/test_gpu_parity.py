@@ -349,6 +349,33 @@ def test_kdline_pick_counts_around_output_blocks(oracle):
             np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, 4, 0), err_msg=f"k={k} cloud {b}")
 
 
+def test_gpu_resident_arrays_through_the_python_api(oracle):
+    """arrays that already live in HBM (anything with __cuda_array_interface__, here torch tensors)
+    are sampled where they are -- same indices as the host-array call, for every entry point."""
+    import torch
+    pcs = synth.uniform_batch(4400, 12, 4096, 3)
+    dp = torch.from_numpy(pcs).cuda()
+    st = [int(x) for x in (np.arange(12) * 5) % 4096]
+    before = capi.kernel_launches()
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling_batch(dp, 300, 5, st), fps.bucket_fps_kdline_sampling_batch(pcs, 300, 5, st))
+    np.testing.assert_array_equal(fps.fps_sampling_batch(dp, 200, 3), fps.fps_sampling_batch(pcs, 200, 3))
+    np.testing.assert_array_equal(fps.bucket_fps_kdtree_sampling_batch(dp, 100), fps.bucket_fps_kdtree_sampling_batch(pcs, 100))
+    assert capi.kernel_launches() > before
+    one = dp[3]
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling(one, 500, 5, start_idx=9), oracle.kdline(pcs[3], 500, 5, 9))
+    np.testing.assert_array_equal(fps.fps_sampling(one, 500, start_idx=9), oracle.fps_vanilla(pcs[3], 500, 9))
+    np.testing.assert_array_equal(fps.bucket_fps_kdtree_sampling(one, 64, start_idx=1), oracle.kdtree(pcs[3], 64, 1))
+    # produced on the device right before the call, on torch's stream: the library waits for it
+    fresh = dp * 2.0 + 1.0
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling_batch(fresh, 64, 4), fps.bucket_fps_kdline_sampling_batch(fresh.cpu().numpy(), 64, 4))
+    with pytest.raises(TypeError):
+        fps.fps_sampling_batch(dp.double(), 10)                     # no implicit cast on the device
+    with pytest.raises(TypeError):
+        fps.fps_sampling_batch(dp.transpose(1, 2), 10)              # not C-contiguous
+    big = torch.from_numpy(synth.uniform_batch(4500, 3, 20000, 3)).cuda()    # the grouped grid sampler reads it too
+    np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling_batch(big, 256, 7), fps.bucket_fps_kdline_sampling_batch(big.cpu().numpy(), 256, 7))
+
+
 def test_device_pointer_entries(oracle):
     import torch
     B, n, d, k, h = 6, 5000, 3, 400, 5

@@ -146,3 +146,26 @@ def test_no_cpu_fallback_without_gpu():
         with pytest.raises(RuntimeError, match="error code 4"):   # FPS_ERR_NO_DEVICE
             call()
     assert "no CPU fallback" in capi.lib().fps_b200_last_error().decode()
+
+
+def test_cuda_array_interface_is_validated_on_the_host():
+    """device arrays are taken as they are: float32, C-contiguous, right rank -- anything else is refused before any
+    pointer reaches the library (no GPU needed for the checks)."""
+    import fpsample_b200 as fps
+
+    class Dev:
+        def __init__(self, shape, typestr="<f4", strides=None):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (0x7f0000000000, False),
+                                             "version": 3, "strides": strides}
+
+    assert fps._cuda_view(np.zeros((4, 3), np.float32), 2) is None           # host arrays take the usual path
+    assert fps._cuda_view(Dev((2, 100, 3)), 3) == (0x7f0000000000, (2, 100, 3))
+    assert fps._cuda_view(Dev((100, 3), strides=(12, 4)), 2) == (0x7f0000000000, (100, 3))
+    with pytest.raises(TypeError):
+        fps._cuda_view(Dev((100, 3), typestr="<f8"), 2)
+    with pytest.raises(TypeError):
+        fps._cuda_view(Dev((100, 3), strides=(4, 400)), 2)
+    with pytest.raises(ValueError):
+        fps._cuda_view(Dev((100, 3)), 3)
+    with pytest.raises(AssertionError):
+        fps.bucket_fps_kdline_sampling_batch(Dev((2, 100, 3)), 200, 3)       # n_samples > n_pts, before any device call
