@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
 CU = ["vanilla.cu", "kdtree.cu", "kdline.cu", "kdsmall.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_dist.cu", "kdline_grid.cu", "kdbuild.cu", "capi.cu"]
-HDR = ["common.cuh", "kdcommon.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
+HDR = ["common.cuh", "kdcommon.cuh", "seqsum.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
 
 
 def _newer(target: str, deps) -> bool:

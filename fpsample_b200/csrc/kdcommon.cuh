@@ -2,6 +2,7 @@
 // the whole grid per level).
 #pragma once
 #include "common.cuh"
+#include "seqsum.cuh"
 
 namespace fps {
 
@@ -231,6 +232,8 @@ __device__ __forceinline__ float seq_sum_tma(const float *src, u32 count, float 
             }
             mbar_wait_cluster(smem_u32(&bars[st]), (phase >> st) & 1u);
             phase ^= 1u << st;
+            // the tile as one integer prefix scan where the running sum stays inside its binade (seqsum.cuh), else the chain
+            if (seq_sum_tile<SS_TILE / 32>(smem_u32(ring + st * SS_TILE), sum)) continue;
             const float4 *p = reinterpret_cast<const float4 *>(ring + st * SS_TILE);
             float4 a[8];
 #pragma unroll

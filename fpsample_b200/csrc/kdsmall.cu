@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) kdsmall_kernel(KdSmallArg
                         const float s = __fsub_rn(ord2f(b[dim + c]), ord2f(b[c]));
                         if (s > span) span = s, sd = c;
                     }
-                    const float sum = ks_seq_sum(smem_u32(q + sd * npad + lo), count);
+                    const float sum = seq_sum_shared<16>(smem_u32(q + sd * npad + lo), count);   // tiles of 512 (seqsum.cuh)
                     const float val = __fdiv_rn(sum, __uint2float_rn(count));
                     __syncwarp();   // every lane has read the node's box
                     if (lane == 0) nval[nn + j] = __float_as_uint(val), nsd[nn + j] = sd;
