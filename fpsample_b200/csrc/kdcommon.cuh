@@ -221,6 +221,7 @@ __device__ __forceinline__ float seq_sum_tma(const float *src, u32 count, float 
                 tma_bulk_g2s(smem_u32(ring + s * SS_TILE), tsrc + (size_t)s * SS_TILE, SS_TILE * 4, smem_u32(&bars[s]));
             }
         }
+        u32 tie_hint = 0;
         for (u32 t = 0; t < ntile; ++t) {
             const u32 st = t % SS_STAGES;
             __syncwarp();   // everybody is done with the stage that is refilled next
@@ -233,7 +234,7 @@ __device__ __forceinline__ float seq_sum_tma(const float *src, u32 count, float 
             mbar_wait_cluster(smem_u32(&bars[st]), (phase >> st) & 1u);
             phase ^= 1u << st;
             // the tile as one integer prefix scan where the running sum stays inside its binade (seqsum.cuh), else the chain
-            if (seq_sum_tile<SS_TILE / 32>(smem_u32(ring + st * SS_TILE), sum)) continue;
+            if (seq_sum_tile<SS_TILE / 32>(smem_u32(ring + st * SS_TILE), sum, tie_hint)) continue;
             const float4 *p = reinterpret_cast<const float4 *>(ring + st * SS_TILE);
             float4 a[8];
 #pragma unroll

@@ -45,8 +45,9 @@ __device__ __forceinline__ float sq_chain16(u32 a, u32 cnt, float sum) {
 
 // One tile of 32 * EPL floats at the 16-byte aligned shared address `a`, summed onto `s` (warp-uniform) exactly as the
 // sequential chain would.  Returns false (s untouched) when the tile does not satisfy the integer model.
+// hint: carried by the caller from tile to tile of one column (start at 0): non-zero after a tile that met an exact tie.
 template <int EPL>
-__device__ __forceinline__ bool seq_sum_tile(u32 a, float &s) {
+__device__ __forceinline__ bool seq_sum_tile(u32 a, float &s, u32 &hint) {
     static_assert(EPL % 4 == 0 && EPL >= 4 && EPL <= 32, "a lane reads whole float4s");
     const u32 lane = lane_id();
     const u32 ef = (__float_as_uint(s) >> 23) & 0xffu;
@@ -59,36 +60,68 @@ __device__ __forceinline__ bool seq_sum_tile(u32 a, float &s) {
     u32 q = 0;                                                       // parity of the running k, "even on entry"
     bool seen = false, bad = false;
     const u32 base = a + lane * (u32)(EPL * 4);
+    bool with_ties = hint != 0;   // the previous tile of this column had an exact tie: expect more, skip the tie-free pass
+    if (!with_ties) {
+        // tie-free pass: everything on the FP32 pipe, integers held in floats (|v| < 2^19 and EPL <= 32 keep every
+        // partial sum below 2^24, so the float additions are exact)
+        float smf = 0.0f, mnf = __int_as_float(0x7f800000), mxf = __int_as_float(0xff800000), vmax = 0.0f;
+        bool anytie = false;
 #pragma unroll
-    for (int t = 0; t < EPL / 4; ++t) {
-        const float4 f = sq_lds128(base + 16u * t);
-        const float x[4] = {f.x, f.y, f.z, f.w};
+        for (int t = 0; t < EPL / 4; ++t) {
+            const float4 f = sq_lds128(base + 16u * t);
+            const float x[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float v = __fmul_rn(x[c], scale);                  // exact (power of two) unless it overflows: caught below
-            bad = bad || !(fabsf(v) < 1048576.0f);                   // also catches nan
-            // round to nearest even integer on the FP32 pipe (no F2I / I2F): adding 1.5 * 2^23 leaves the integer in the
-            // low mantissa bits, valid for |v| < 2^22
-            const float tm = __fadd_rn(v, 12582912.0f);
-            const int r = (__float_as_int(tm) & 0x7fffff) - 0x400000;
-            const float d = __fsub_rn(v, __fsub_rn(tm, 12582912.0f)); // exact
-            const bool tie = fabsf(d) == 0.5f;
-            const int alt = r + (d > 0.0f ? 1 : -1);                 // the other neighbour of a tie
-            const int inc = (tie && q) ? alt : r;                    // r is the even neighbour: right when k is even
-            if (tie && !seen) {
-                dlt = (q ? r : alt) - inc;                           // what "odd on entry" adds here instead
-                seen = true;
+            for (int c = 0; c < 4; ++c) {
+                const float v = __fmul_rn(x[c], scale);              // exact (power of two) unless it overflows: caught below
+                vmax = fmaxf(vmax, fabsf(v));
+                // round to the nearest even integer without F2I / I2F: adding 1.5 * 2^23 leaves the integer in the low
+                // mantissa bits (valid for |v| < 2^22)
+                const float rf = __fsub_rn(__fadd_rn(v, 12582912.0f), 12582912.0f);
+                anytie = anytie || fabsf(__fsub_rn(v, rf)) == 0.5f;
+                smf = __fadd_rn(smf, rf);
+                mnf = fminf(mnf, smf);
+                mxf = fmaxf(mxf, smf);
             }
-            q = tie ? 0u : (q ^ (u32)(inc & 1));
-            sm += inc;
-            mn = min(mn, sm);
-            mx = max(mx, sm);
+        }
+        // fmaxf drops a nan operand, but a nan (or inf - inf) reaches smf; anything too large for the model trips vmax
+        bad = !(vmax < 524288.0f) || !(fabsf(smf) < 16777216.0f);
+        if (__any_sync(FULL, bad)) return false;
+        sm = __float2int_rn(smf), mn = __float2int_rn(mnf), mx = __float2int_rn(mxf);
+        q = (u32)sm & 1u;
+        with_ties = __any_sync(FULL, anytie);
+    }
+    if (with_ties) {   // the full rule, every lane (a tie's rounding depends on the parity of the running sum)
+        sm = 0, mn = 0x7fffffff, mx = (int)0x80000000, q = 0;
+#pragma unroll
+        for (int t = 0; t < EPL / 4; ++t) {
+            const float4 f = sq_lds128(base + 16u * t);
+            const float x[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float v = __fmul_rn(x[c], scale);
+                bad = bad || !(fabsf(v) < 524288.0f);                // also catches nan
+                const float tm = __fadd_rn(v, 12582912.0f);
+                const int r = (__float_as_int(tm) & 0x7fffff) - 0x400000;
+                const float d = __fsub_rn(v, __fsub_rn(tm, 12582912.0f));   // exact
+                const bool tie = fabsf(d) == 0.5f;
+                const int alt = r + (d > 0.0f ? 1 : -1);             // the other neighbour of a tie
+                const int inc = (tie && q) ? alt : r;                // r is the even neighbour: right when k is even
+                if (tie && !seen) {
+                    dlt = (q ? r : alt) - inc;                       // what "odd on entry" adds here instead
+                    seen = true;
+                }
+                q = tie ? 0u : (q ^ (u32)(inc & 1));
+                sm += inc;
+                mn = min(mn, sm);
+                mx = max(mx, sm);
+            }
         }
     }
     if (__any_sync(FULL, bad)) return false;
 
     // parity on entry of every lane: the last lane below with a tie fixes it, lanes without one flip it by their sum
     const u32 C = __ballot_sync(FULL, seen), V = __ballot_sync(FULL, q & 1u);
+    hint = C;
     const u32 below = (1u << lane) - 1u, cm = C & below;
     u32 p, span;
     if (cm) {
@@ -122,14 +155,14 @@ template <int EPL>
 __device__ __forceinline__ float seq_sum_shared(u32 a, u32 count) {
     constexpr u32 TILE = 32u * EPL;
     float sum = 0.0f;
-    u32 i = 0;
+    u32 i = 0, hint = 0;
     while (i < count && ((a + 4u * i) & 15u)) {   // up to 3 values
         float f;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(a + 4u * i));
         sum = __fadd_rn(sum, f), ++i;
     }
     for (; i + TILE <= count; i += TILE)
-        if (!seq_sum_tile<EPL>(a + 4u * i, sum)) sum = sq_chain16(a + 4u * i, TILE, sum);
+        if (!seq_sum_tile<EPL>(a + 4u * i, sum, hint)) sum = sq_chain16(a + 4u * i, TILE, sum);
     const u32 rest16 = (count - i) & ~15u;
     if (rest16) sum = sq_chain16(a + 4u * i, rest16, sum), i += rest16;
     for (; i < count; ++i) {

@@ -14,7 +14,7 @@ template <int EPL, bool FAST>
 __global__ void k(const float *x, u32 n, float *out, long long *cyc, u32 *nfast) {
     __shared__ __align__(16) float buf[CH];
     float sum = 0.0f;
-    u32 fast = 0, tiles = 0;
+    u32 fast = 0, tiles = 0, hint = 0;
     long long t = 0;
     for (u32 i0 = 0; i0 < n; i0 += CH) {
         const u32 m = min((u32)CH, n - i0);
@@ -26,7 +26,7 @@ __global__ void k(const float *x, u32 n, float *out, long long *cyc, u32 *nfast)
         constexpr u32 TILE = 32 * EPL;
         for (; i + TILE <= m; i += TILE) {
             ++tiles;
-            if (FAST && seq_sum_tile<EPL>(a + 4 * i, sum)) ++fast;
+            if (FAST && seq_sum_tile<EPL>(a + 4 * i, sum, hint)) ++fast;
             else sum = sq_chain16(a + 4 * i, TILE, sum);
         }
         for (; i < m; ++i) sum = __fadd_rn(sum, buf[i]);
