@@ -26,6 +26,7 @@ EXPORTS = {
     "fps_b200_vanilla_batch_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "fps_b200_kdline_batch_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "fps_b200_kdline_build_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
+    "fps_b200_seqsum_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "fps_b200_device_count": (ctypes.c_int, []),
     "fps_b200_version": (ctypes.c_char_p, []),
     "fps_b200_last_error": (ctypes.c_char_p, []),
@@ -196,6 +197,10 @@ def kdtree_batch_dev(d_pts, b, n, d, k, d_start, d_out, d_ws, ws_bytes, stream=0
 def kdline_build_dev(d_pts, b, n, d, h, d_perm, d_leaf_lo, d_leaf_box, d_ws, ws_bytes, stream=0):
     _check("fps_b200_kdline_build_dev", lib().fps_b200_kdline_build_dev(
         d_pts, b, n, d, h, d_perm, d_leaf_lo or None, d_leaf_box or None, d_ws or None, ws_bytes, stream or None))
+
+
+def seqsum_dev(d_values, n, d_sum, d_fast_tiles=0, tile=512, stream=0):
+    _check("fps_b200_seqsum_dev", lib().fps_b200_seqsum_dev(d_values, n, d_sum, d_fast_tiles or None, tile, stream or None))
 
 
 def pinned_empty(shape, dtype):

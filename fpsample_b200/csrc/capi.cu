@@ -1008,4 +1008,17 @@ int fps_b200_kdline_build_dev(const float *d_points, size_t B, size_t n, size_t 
                           workspace_bytes, n_sms, static_cast<cudaStream_t>(stream));
 }
 
+int fps_b200_seqsum_dev(const float *d_values, size_t n, float *d_sum, uint32_t *d_fast_tiles, int tile, void *stream) {
+    if (!d_values || !d_sum || n == 0 || (tile != 256 && tile != 512)) {
+        set_err("bad argument: need values/sum non-null, n >= 1, tile 256 or 512");
+        return FPS_ERR_ARG;
+    }
+    if (n_sms_current(nullptr) <= 0) {
+        set_err("current device is not a usable sm_100 device; there is no CPU fallback");
+        return FPS_ERR_NO_DEVICE;
+    }
+    CK(launch_seqsum(d_values, n, d_sum, d_fast_tiles, tile / 32, static_cast<cudaStream_t>(stream)));
+    return FPS_OK;
+}
+
 }  // extern "C"

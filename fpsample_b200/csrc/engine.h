@@ -151,6 +151,9 @@ cudaError_t launch_kdtree_build(const float *pts, unsigned char *region, size_t 
 cudaError_t launch_kdtree_map(u64 *out, const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 k, u32 dim,
                               cudaStream_t st);
 
+// ---- test entry for the tile-parallel sequential sum (seqsum.cu) ------------------------------------------------------
+cudaError_t launch_seqsum(const float *x, size_t n, float *out, u32 *fast_tiles, int epl, cudaStream_t st);
+
 void count_launch();
 
 }  // namespace fps

@@ -108,6 +108,13 @@ FPS_API int fps_b200_kdline_build_dev(const float *d_points, size_t B, size_t n,
                               uint32_t *d_perm, uint32_t *d_leaf_lo, float *d_leaf_box,
                               void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* The kd build's split value (testing / inspection): d_sum[0] = the STRICTLY SEQUENTIAL binary32 sum of d_values[0..n)
+ * (`float s = 0; for (...) s += x;`, src/_ext/KDTreeBase.h:151-158), evaluated by one warp through the tile-parallel code
+ * of the build kernels (csrc/seqsum.cuh; tile = 256 or 512 elements).  d_fast_tiles (may be NULL) receives how many tiles
+ * took the integer prefix-scan path instead of the dependent add chain. */
+FPS_API int fps_b200_seqsum_dev(const float *d_values, size_t n, float *d_sum, uint32_t *d_fast_tiles, int tile,
+                        void *stream);
+
 /* ---- utilities ---------------------------------------------------------------------------------- */
 
 FPS_API int fps_b200_device_count(void);            /* usable (sm_100) devices; 0 if none                     */

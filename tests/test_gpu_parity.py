@@ -376,6 +376,39 @@ def test_gpu_resident_arrays_through_the_python_api(oracle):
     np.testing.assert_array_equal(fps.bucket_fps_kdline_sampling_batch(big, 256, 7), fps.bucket_fps_kdline_sampling_batch(big.cpu().numpy(), 256, 7))
 
 
+def test_sequential_sum_tiles_are_bit_exact():
+    """the split value is a strictly sequential binary32 sum (KDTreeBase.h:151-158); the build kernels evaluate it tile by
+    tile as an integer prefix scan (csrc/seqsum.cuh).  Bit-equal to numpy's sequential float32 accumulate on columns
+    that hit every branch: single-signed, zero-mean, exact ties, lattices, wild magnitudes, inf."""
+    import torch
+    g = np.random.default_rng(77)
+    n = 300_000
+    lid = synth.lidar(31, n)
+    cols = {
+        "uniform": synth.uniform(5, n, 3)[:, 0], "uniform-0.5": synth.uniform(6, n, 3)[:, 1] - np.float32(0.5),
+        "lidar x": lid[:, 0], "lidar y": lid[:, 1], "lidar z": lid[:, 2], "sorted lidar x": np.sort(lid[:, 0]),
+        "halves": (g.integers(-50, 50, n) * 0.5).astype(np.float32), "quarters": (g.integers(0, 64, n) * 0.25).astype(np.float32),
+        "lattice": synth.grid_ties(3, n, 3)[:, 1], "gauss": (g.standard_normal(n) * 30).astype(np.float32),
+        "mixed": np.where(np.arange(n) % 97 == 0, g.random(n) * 1e6, g.random(n) * 1e-3).astype(np.float32),
+        "tiny": (g.random(n) * 1e-30).astype(np.float32), "huge": (g.random(n) * 1e30).astype(np.float32),
+        "inf": np.where(np.arange(n) == 200_000, np.inf, g.random(n)).astype(np.float32),
+        "short": synth.uniform(8, 700, 3)[:, 2], "one": np.array([3.25], np.float32),
+    }
+    out = torch.zeros(1, dtype=torch.float32, device="cuda")
+    fast = torch.zeros(1, dtype=torch.int32, device="cuda")
+    some_fast = 0
+    for name, col in cols.items():
+        col = np.ascontiguousarray(col, dtype=np.float32)
+        want = np.add.accumulate(col, dtype=np.float32)[-1]           # strictly sequential
+        d = torch.from_numpy(col).cuda()
+        for tile in (256, 512):
+            capi.seqsum_dev(d.data_ptr(), col.size, out.data_ptr(), fast.data_ptr(), tile, torch.cuda.current_stream().cuda_stream)
+            got = out.cpu().numpy()[0]
+            assert got.tobytes() == want.tobytes(), f"{name} tile={tile}: {got!r} != {want!r}"
+            some_fast += int(fast.cpu().numpy()[0])
+    assert some_fast > 1000   # the scan path really ran
+
+
 def test_device_pointer_entries(oracle):
     import torch
     B, n, d, k, h = 6, 5000, 3, 400, 5
