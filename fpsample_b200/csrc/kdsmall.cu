@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) kdsmall_kernel(KdSmallArg
 #pragma unroll
                 for (int c = 0; c < DIM; ++c) mnL[c] = mnR[c] = PINF, mxL[c] = mxR[c] = NINF;
                 u32 cnt = 0;
+#pragma unroll 4
                 for (u32 i = s0 + lane; i < s1; i += 32) {
                     const bool f = col[i] < val;
                     cnt += f ? 1u : 0u;
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(T, T == 256 ? 3 : 1) kdsmall_kernel(KdSmallArg
                 if (m != 0 && m != count) {
                     const u32 chunk = roundup32((count + ts - 1) / ts);
                     const u32 s0 = min(hi, lo + rank * chunk), s1 = min(hi, s0 + chunk);
+#pragma unroll 4
                     for (u32 i0 = s0; i0 < s1; i0 += 32) {
                         const u32 i = i0 + lane;
                         const bool in = i < s1;
