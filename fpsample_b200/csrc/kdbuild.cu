@@ -258,17 +258,32 @@ __global__ void __launch_bounds__(256) gb_swap(GBArgs a) {
     const u32 lo = it.lo, hi = it.hi, count = hi - lo;
     const u32 g = v.A3[it.j], m = v.A2[it.j];
     const u32 k1 = min(g, (it.r + 1) * GB_WCH);
-    for (u32 kk = it.r * GB_WCH + lane; kk < k1; kk += 32) {
-        const u32 pa = v.scr[lo + kk], pb = v.scr[hi - 1 - kk];
+    // four pairs per lane in flight: the swap is a chain of dependent random accesses (list -> rows) into L2 / HBM
+    for (u32 kk0 = it.r * GB_WCH + lane; kk0 < k1; kk0 += 128) {
+        u32 pa[4], pb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const u32 kk = kk0 + 32 * u;
+            pa[u] = kk < k1 ? v.scr[lo + kk] : 0xffffffffu;
+            pb[u] = kk < k1 ? v.scr[hi - 1 - kk] : 0xffffffffu;
+        }
         for (u32 c = 0; c < a.dim; ++c) {
             float *col = v.q + (size_t)c * a.npad;
-            const float xa = col[pa], xb = col[pb];
-            col[pa] = xb;
-            col[pb] = xa;
+            float xa[4], xb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (pa[u] != 0xffffffffu) xa[u] = col[pa[u]], xb[u] = col[pb[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (pa[u] != 0xffffffffu) col[pa[u]] = xb[u], col[pb[u]] = xa[u];
         }
-        const u32 ia = v.perm[pa], ib = v.perm[pb];
-        v.perm[pa] = ib;
-        v.perm[pb] = ia;
+        u32 ia[4], ib[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pa[u] != 0xffffffffu) ia[u] = v.perm[pa[u]], ib[u] = v.perm[pb[u]];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (pa[u] != 0xffffffffu) v.perm[pa[u]] = ib[u], v.perm[pb[u]] = ia[u];
     }
     if (it.r == 0) {
         const u32 lim = m == 0 ? 1u : (m == count ? count - 1 : m);   // KDTreeBase.h:142-146
