@@ -301,6 +301,14 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         L->region_stride = kd_region_bytes(n, dim, h);
         L->counter_off = L->region_off + B * L->region_stride;
         L->total = L->counter_off + 256;
+        // clouds that stay in global memory: the grid-wide per-level launches build a batch faster than one CTA per
+        // cloud working out of L2 (scripts/cmp_build5.py)
+        L->gridbuild = !L->small && L->wp.global;
+        if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = !L->small && atoi(e) != 0;
+        if (L->gridbuild) {
+            L->aux_off = (L->total + 255) & ~(size_t)255;
+            L->total = L->aux_off + B * kd_gridbuild_aux_bytes(n, dim, h);
+        }
         return cudaSuccess;
     }
     // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
@@ -312,7 +320,9 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
     L->async = !build_only && !L->grid && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
     if (L->async || L->dist || L->grid) {
         // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
-        L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144;
+        // ... and so is any batch of clouds the per-cloud kernel would have to work on out of L2 (100 k-point clouds:
+        // 128 clouds 2.9 -> 2.1 ms, 512 clouds 10.9 -> 6.4 ms, scripts/cmp_build5.py)
+        L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144 || !(L->pl.in_smem & 1);
         if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
         // a cloud whose coordinates fit one SM's shared memory is built by one CTA (kdsmall_kernel, 1024 threads): about
         // 0.1 ms per wave of 148 clouds against 49 grid-wide launches (0.77 ms at BASELINE.json cfg 3)
