@@ -68,7 +68,7 @@ __device__ __forceinline__ void sts64(u32 a, float x, float y) {
 // ---- the two point stores ---------------------------------------------------------------------------------------
 // component c (0..DIM-1 coordinates, DIM = running distance) of position (chunk, lane)
 struct SmemStore {
-    static constexpr bool kTrackCoords = false, kCoordsInPlace = false;
+    static constexpr bool kTrackCoords = false, kCoordsInPlace = false, kWide = false;
     u32 base;   // shared-space byte address of this warp's slot
     u32 lst;    // words per (component, lane) row: nch + 4 (16-byte aligned rows, conflict-free 128-bit access)
     __device__ __forceinline__ u32 addr(u32 comp, u32 lane, u32 chunk) const { return base + ((comp * 32u + lane) * lst + chunk) * 4u; }
@@ -111,7 +111,7 @@ struct SmemStore {
 struct TmemStore {
     // a point lookup is three tcgen05.ld + a wait + three shuffles on the pick path: lanes remember their candidate's
     // coordinates instead (three selects per chunk of a bucket pass) and the winner broadcasts them
-    static constexpr bool kTrackCoords = true, kCoordsInPlace = false;
+    static constexpr bool kTrackCoords = true, kCoordsInPlace = false, kWide = false;
     u32 base;   // tensor-memory address of this warp's lane quarter: (32 * (warp % 4)) << 16 | first column
     u32 nch;    // columns per component
     __device__ __forceinline__ void ld4(u32 col, u32 *w) const {
@@ -174,7 +174,7 @@ struct TmemStore {
 // (BASELINE.json cfg 3) is 192 KB of coordinates + 64 KB of distances -- more than either store alone, exactly what one
 // SM has when both are used.  One such warp per SM (its distances fill one lane quarter of TMEM).
 struct HybridStore {
-    static constexpr bool kTrackCoords = false, kCoordsInPlace = false;
+    static constexpr bool kTrackCoords = false, kCoordsInPlace = false, kWide = false;
     SmemStore s;   // DIM components
     TmemStore t;   // one component: the distance of chunk c is column c
     u32 dimc;      // index of the distance component (= DIM of the kernel)
@@ -199,9 +199,11 @@ struct HybridStore {
 // Points stay in the per-cloud region in global memory (L2 / HBM): for big clouds in big batches, where throughput
 // comes from hundreds of clouds in flight (one warp each) and the governing roofline is HBM bandwidth -- 4(D+2)
 // bytes per point-update.  A warp access is 32 consecutive positions = one 128-byte line per component.
-struct GlobalStore {
+template <bool WIDE>
+struct GlobalStoreT {
     static constexpr bool kTrackCoords = true;   // a point lookup would be an L2 / HBM round trip on the pick path
     static constexpr bool kCoordsInPlace = true; // the region already holds the coordinates: only distances are staged
+    static constexpr bool kWide = WIDE;          // 16-chunk blocks (few clouds per SM: bytes in flight per warp matter)
     const float *q;   // [dim][npad]
     float *dis;       // [npad]
     u32 npad, n;
@@ -424,7 +426,14 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
             } else if (ncn <= 6) {
                 block(std::integral_constant<int, 6>{}, min(c0, nch - 6u));
             } else {
-                for (u32 cb0 = c0 & ~3u; cb0 <= c1b; cb0 += W_U) block(std::integral_constant<int, W_U>{}, min(cb0, nch - W_U));
+                u32 cb0 = c0 & ~3u;
+                if constexpr (ST::kWide) {
+                    // points in global memory: a block's loads are one L2 / HBM round trip, so the big buckets of big clouds
+                    // go in blocks of 16 chunks (twice the bytes in flight per warp, half the round trips per bucket pass)
+                    if (nch >= 16)
+                        for (; cb0 + 8 <= c1b; cb0 += 16) block(std::integral_constant<int, 16>{}, min(cb0, nch - 16u));
+                }
+                for (; cb0 <= c1b; cb0 += W_U) block(std::integral_constant<int, W_U>{}, min(cb0, nch - W_U));
             }
             st.wait_st();   // a neighbouring bucket may share this bucket's first / last chunk
             // bucket max, then its lowest position; the owner lane takes both plus the point's coordinates
@@ -579,7 +588,7 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_warpg_kernel(WarpArgs a) {
     u32 cloud = warp * gridDim.x + blockIdx.x;
     while (cloud < a.B) {
         unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
-        GlobalStore st;
+        GlobalStoreT<(MAXT == 256 && DIM <= 4)> st;
         st.q = reinterpret_cast<const float *>(rg);
         st.dis = reinterpret_cast<float *>(rg) + (size_t)a.dim * a.npad;
         st.npad = a.npad;
@@ -657,7 +666,9 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         // long pending lists matter more than warps per SM here: every early flush re-reads a bucket from HBM, and in
         // 6-D the reference itself defers ~14 samples per pick.  Warps per CTA = what the lists
         // leave room for (at least 4: each warp keeps (D+1) x 8 lines in flight).
-        const u32 maxt = dimp <= 4 ? 512 : 256;
+        // many clouds per SM: 16 warps per CTA with 8-chunk blocks; fewer (an 8-GPU shard of cfg 5 is 3.5 per SM): 8 warps
+        // with 16-chunk blocks -- twice the bytes in flight per warp (512 x 100 k: 81.8 -> 60.7 ms; 4096: 224 vs 269 ms)
+        const u32 maxt = (dimp <= 4 && B > (size_t)8 * n_sms) ? 512 : 256;   // up to one wave of 8-warp CTAs
         size_t R = lazy ? (dimp <= 4 ? 6 : W_MAXR) : 1;
         size_t nwg = maxt / 32;
         while (nwg > 4 && nwg * meta_of(R) > cap) --nwg;
@@ -749,10 +760,14 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;
     if (pl.global) {
+        const bool wide = pl.n_smem_warps <= 8;   // the plan's CTA size picks the variant
         switch (pl.dimp) {
-            case 2: e = b1 ? launch_warpg_t<2, 1, 512>(pl, a, st) : launch_warpg_t<2, 4, 512>(pl, a, st); break;
-            case 3: e = b1 ? launch_warpg_t<3, 1, 512>(pl, a, st) : launch_warpg_t<3, 4, 512>(pl, a, st); break;
-            case 4: e = b1 ? launch_warpg_t<4, 1, 512>(pl, a, st) : launch_warpg_t<4, 4, 512>(pl, a, st); break;
+            case 2: e = wide ? (b1 ? launch_warpg_t<2, 1, 256>(pl, a, st) : launch_warpg_t<2, 4, 256>(pl, a, st))
+                         : (b1 ? launch_warpg_t<2, 1, 512>(pl, a, st) : launch_warpg_t<2, 4, 512>(pl, a, st)); break;
+            case 3: e = wide ? (b1 ? launch_warpg_t<3, 1, 256>(pl, a, st) : launch_warpg_t<3, 4, 256>(pl, a, st))
+                         : (b1 ? launch_warpg_t<3, 1, 512>(pl, a, st) : launch_warpg_t<3, 4, 512>(pl, a, st)); break;
+            case 4: e = wide ? (b1 ? launch_warpg_t<4, 1, 256>(pl, a, st) : launch_warpg_t<4, 4, 256>(pl, a, st))
+                         : (b1 ? launch_warpg_t<4, 1, 512>(pl, a, st) : launch_warpg_t<4, 4, 512>(pl, a, st)); break;
             case 6: e = b1 ? launch_warpg_t<6, 1, 256>(pl, a, st) : launch_warpg_t<6, 4, 256>(pl, a, st); break;
             default: e = b1 ? launch_warpg_t<7, 1, 256>(pl, a, st) : launch_warpg_t<7, 4, 256>(pl, a, st); break;
         }
