@@ -262,7 +262,7 @@ struct KdLayout {
 
 // fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
 // and sample with the cluster coordinator/worker kernel
-static size_t tmp_stream_minB(int n_sms) { return ((size_t)11 * n_sms) / 4; }
+static size_t tmp_stream_minB(int n_sms) { return (size_t)2 * n_sms; }
 static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L, bool ids = false) {
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
@@ -280,7 +280,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
         // ... unless the batch is big enough for the one-warp-per-cloud streaming kernel (>= 4 clouds per SM in flight,
         // HBM-bound: BASELINE.json cfg 5) and a cloud would tie up 4 or more SMs
         // (measured on 100 k-point clouds, scripts/cmp_cfg5.py: 16 CTAs per cloud sample 4.7 k clouds/s at any batch size, the
-        // streaming kernel needs ~80 ms however few clouds it gets -- it wins from ~2.75 clouds per SM: 512 clouds 5.5 k/s)
+        // streaming kernel needs ~55 ms however few clouds it gets -- it wins from ~2 clouds per SM: 300 clouds 5.0 k/s, 512 clouds 7.7 k/s)
         const size_t stream_from = tmp_stream_minB(n_sms);
         prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp, ids) && tmp.flat &&
                        (ids || tmp.gc <= 2 || B < (tmp.gc >= 8 ? stream_from : (size_t)4 * n_sms));

@@ -660,7 +660,7 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
     if (sw + tm == 0) {
         // not on chip: points stay in global memory, one warp per cloud, worth it only when the batch keeps every SM
         // busy with many clouds (throughput from clouds in flight, HBM-bound); small batches go to the cluster kernels
-        size_t minB = ((size_t)11 * n_sms) / 4;   // ~2.75 clouds per SM: where it overtakes 16-CTA groups on 100 k-point clouds
+        size_t minB = (size_t)2 * n_sms;   // ~2 clouds per SM: where it overtakes 16-CTA groups on 100 k-point clouds (scripts/cmp_cfg5.py)
         if (const char *e = getenv("FPS_B200_WARP_GLOBAL_MINB")) minB = (size_t)atol(e);
         if (B < minB) return false;
         // long pending lists matter more than warps per SM here: every early flush re-reads a bucket from HBM, and in
