@@ -300,7 +300,9 @@ def test_kdline_build_matches_oracle(oracle):
                            (3000, 1, 6, "g"), (3000, 2, 6, "g"), (5000, 2, 7, "g"), (3000, 3, 6, "g"), (4099, 3, 5, "u"),
                            (2000, 5, 4, "u"), (8000, 3, 7, "l"), (4096, 3, 8, "u"),
                            # one CTA of 1024 threads per cloud, index arrays in global memory (cfg 3's shape)
-                           (16384, 3, 7, "u"), (16000, 2, 7, "g"), (12000, 4, 6, "u"), (17000, 3, 8, "g")]:
+                           (16384, 3, 7, "u"), (16000, 2, 7, "g"), (12000, 4, 6, "u"), (17000, 3, 8, "g"),
+                           # the edges of what one SM holds: 16-bit indices up to 65 535 points, 8 dimensions
+                           (50000, 1, 8, "g"), (65535, 1, 5, "u"), (65536, 1, 5, "u"), (6000, 8, 6, "u"), (33, 3, 5, "u")]:
         pc = {"u": lambda: synth.uniform(n, n, d), "l": lambda: synth.lidar(n, n),
               "g": lambda: synth.grid_ties(n, n, d)}[gen]()
         S = 1 << h
