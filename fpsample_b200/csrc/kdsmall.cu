@@ -16,13 +16,15 @@
 //     positions, recomputes its boxes by position,
 //   * drops the block barrier below the level that has one node per warp: from there on a warp owns its subtree and
 //     __syncwarp is all the ordering it needs,
-//   * stages the cloud with 128-bit loads, four in flight per thread.
-// The dependent FADD chain of the mean (4 cycles per element, one warp per node) stays the critical path.
+//   * stages the cloud with 128-bit loads, four in flight per thread,
+//   * evaluates the strictly sequential mean tile by tile as an integer prefix scan where the running sum allows it
+//     (seqsum.cuh), the dependent FADD chain elsewhere.
 #include <cfloat>
 
 #include "common.cuh"
 #include "engine.h"
 #include "kdcommon.cuh"
+#include "seqsum.cuh"
 
 namespace fps {
 
@@ -33,42 +35,6 @@ struct KdSmallArgs {
     unsigned short *idx_ws;  // IDXG: per resident CTA, permutation + misplaced-position scratch (2 * npad u16) in global memory
     u32 B, n, dim, h;
 };
-
-__device__ __forceinline__ float4 ks_lds128(u32 a) {
-    float4 f;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(a));
-    return f;
-}
-__device__ __forceinline__ float ks_lds(u32 a) {
-    float f;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(f) : "r"(a));
-    return f;
-}
-
-// strictly sequential binary32 sum of `count` floats at shared address `a` (KDTreeBase.h:151-158): every lane runs the
-// same chain over broadcast 128-bit loads, the next 16 values are loaded while the current 16 are added
-__device__ __forceinline__ float ks_seq_sum(u32 a, u32 count) {
-    float sum = 0.0f;
-    u32 i = 0;
-    while (i < count && ((a + 4u * i) & 15u)) sum = __fadd_rn(sum, ks_lds(a + 4u * i)), ++i;   // up to 3 values
-    const u32 p = a + 4u * i;
-    const u32 nblk = (count - i) >> 4;
-    if (nblk) {
-        float4 a0 = ks_lds128(p), a1 = ks_lds128(p + 16u), a2 = ks_lds128(p + 32u), a3 = ks_lds128(p + 48u);
-        for (u32 b = 1; b <= nblk; ++b) {
-            const u32 nb = p + 64u * (b < nblk ? b : b - 1);   // the last round reloads its own block: no branch in the chain
-            const float4 n0 = ks_lds128(nb), n1 = ks_lds128(nb + 16u), n2 = ks_lds128(nb + 32u), n3 = ks_lds128(nb + 48u);
-            sum = __fadd_rn(sum, a0.x), sum = __fadd_rn(sum, a0.y), sum = __fadd_rn(sum, a0.z), sum = __fadd_rn(sum, a0.w);
-            sum = __fadd_rn(sum, a1.x), sum = __fadd_rn(sum, a1.y), sum = __fadd_rn(sum, a1.z), sum = __fadd_rn(sum, a1.w);
-            sum = __fadd_rn(sum, a2.x), sum = __fadd_rn(sum, a2.y), sum = __fadd_rn(sum, a2.z), sum = __fadd_rn(sum, a2.w);
-            sum = __fadd_rn(sum, a3.x), sum = __fadd_rn(sum, a3.y), sum = __fadd_rn(sum, a3.z), sum = __fadd_rn(sum, a3.w);
-            a0 = n0, a1 = n1, a2 = n2, a3 = n3;
-        }
-        i += nblk << 4;
-    }
-    for (; i < count; ++i) sum = __fadd_rn(sum, ks_lds(a + 4u * i));
-    return sum;
-}
 
 // tight box of positions [s0, s1) by one warp, written (not folded) to box[0..2*dim): lows then highs, ordered ints
 template <int DIM>
