@@ -15,6 +15,7 @@ import fails loudly when the native extension has not been built (python build_n
 """
 from __future__ import annotations
 
+import warnings
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -28,6 +29,7 @@ try:
         _bucket_fps_kdtree_sampling_batch,
         _batch_ptr,
         _device_count,
+        _fps_npdu_sampling,
         _fps_sampling,
         _fps_sampling_batch,
         _kernel_launches,
@@ -256,7 +258,29 @@ def _out_of_scope(name):
     return f
 
 
-fps_npdu_sampling = _out_of_scope("fps_npdu_sampling")
+def fps_npdu_sampling(pc: np.ndarray, n_samples: int, w: Optional[int] = None,
+                      start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
+    """FPS with the nearest-point-distance-updating heuristic over an index window (reference:
+    src/fpsample/__init__.py:66-103 -> src/lib.cpp:272-366).  NOT exact FPS; needs dimensional locality, like the reference.
+
+    w: window size of the local update, default n_pts / n_samples * 16 (capped to n_pts - 1 with the reference's warning).
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pc.ndim == 2
+    n_pts, _ = pc.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    assert start_idx is None or 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    if isinstance(start_idx, list):
+        assert len(start_idx) <= n_samples, "len(start_idx) should be <= n_samples"
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    w = w or int(n_pts / n_samples * 16)
+    if w >= n_pts - 1:
+        warnings.warn(f"k is too large, set to {n_pts - 1}")
+        w = n_pts - 1
+    start_idx = get_start_idx(n_pts, start_idx)
+    return _fps_npdu_sampling(pc, n_samples, w, start_idx)
+
+
 fps_npdu_kdtree_sampling = _out_of_scope("fps_npdu_kdtree_sampling")
 
 __all__ = [

@@ -649,7 +649,9 @@ static int run_shard(int dev, const ShardJob &j) {
         const size_t nb = (j.B - b0 < chunk) ? j.B - b0 : chunk;
         Lane &ln = cx->lane[c & 1];
         size_t ws_need;
-        if (j.algo == FPS_ALGO_VANILLA) {
+        if (j.algo == FPS_ALGO_NPDU) {
+            ws_need = npdu_workspace_bytes(nb, j.n);
+        } else if (j.algo == FPS_ALGO_VANILLA) {
             WsLayout L;
             vanilla_layout(nb, j.n, j.dim, cx->n_sms, &L);
             ws_need = L.total;
@@ -672,7 +674,20 @@ static int run_shard(int dev, const ShardJob &j) {
                                cudaMemcpyHostToDevice, ln.st));
         }
         if (!dev_in) CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
-        if (j.algo == FPS_ALGO_VANILLA)
+        if (j.algo == FPS_ALGO_NPDU) {
+            cudaError_t e = launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, static_cast<u64 *>(ln.out.p), ln.ws.p,
+                                        cx->n_sms, ln.st);
+            if (e == cudaErrorNotSupported) {
+                cudaGetLastError();
+                set_err("fps_npdu: dim > 64 or more than 6.5 M points are not supported");
+                rc = FPS_ERR_UNSUPPORTED;
+            } else if (e != cudaSuccess) {
+                set_err("npdu launch failed: %s", cudaGetErrorString(e));
+                rc = FPS_ERR_CUDA + (int)e;
+            } else {
+                set_plan("npdu_kernel clouds=%zu (one CTA per cloud, 256-point segment maxima in shared memory) window=%zu", nb, j.h);
+            }
+        } else if (j.algo == FPS_ALGO_VANILLA)
             rc = enqueue_vanilla(d_in, nb, j.n, j.dim, j.k, d_starts, j.n_starts,
                                  static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else if (j.algo == FPS_ALGO_KDTREE)
@@ -933,6 +948,31 @@ int fps_b200_kdline_batch(const float *points, size_t B, size_t n, size_t dim, s
     if (rc) return rc;
     if ((rc = check_kdline(n, dim, height))) return rc;
     ShardJob j{FPS_ALGO_KDLINE, points, B, n, dim, k, height, start, 1, out};
+    return run_batch(j, devices, n_devices);
+}
+
+int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_samples, size_t window, size_t start_idx, size_t *out) {
+    int rc = check_common(points, 1, n, dim, n_samples, out);
+    if (rc) return rc;
+    if (start_idx >= n) {
+        set_err("start_idx %zu out of range (n=%zu)", start_idx, n);
+        return FPS_ERR_START;
+    }
+    ShardJob j{FPS_ALGO_NPDU, points, 1, n, dim, n_samples, window, &start_idx, 1, out};
+    return run_batch(j, nullptr, 1);
+}
+
+int fps_b200_npdu_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t window,
+                        const size_t *start, size_t *out, const int *devices, int n_devices) {
+    int rc = check_common(points, B, n, dim, n_samples, out);
+    if (rc) return rc;
+    if (start)
+        for (size_t b = 0; b < B; ++b)
+            if (start[b] >= n) {
+                set_err("start[%zu]=%zu out of range (n=%zu)", b, start[b], n);
+                return FPS_ERR_START;
+            }
+    ShardJob j{FPS_ALGO_NPDU, points, B, n, dim, n_samples, window, start, 1, out};
     return run_batch(j, devices, n_devices);
 }
 

@@ -151,6 +151,11 @@ cudaError_t launch_kdtree_build(const float *pts, unsigned char *region, size_t 
 cudaError_t launch_kdtree_map(u64 *out, const unsigned char *region, size_t region_stride, u32 B, u32 n, u32 k, u32 dim,
                               cudaStream_t st);
 
+// ---- fps_npdu_sampling: index-window heuristic, one CTA per cloud (npdu.cu) ---------------------------------------------
+size_t npdu_workspace_bytes(size_t B, size_t n);
+cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t k, size_t w, const u64 *starts, u64 *out,
+                        void *ws, int n_sms, cudaStream_t st);
+
 // ---- test entry for the tile-parallel sequential sum (seqsum.cu) ------------------------------------------------------
 cudaError_t launch_seqsum(const float *x, size_t n, float *out, u32 *fast_tiles, int epl, cudaStream_t st);
 

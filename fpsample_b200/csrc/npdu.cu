@@ -1,0 +1,117 @@
+// npdu.cu -- fps_npdu_sampling: FPS with the reference's "nearest point distance updating"
+// heuristic over an INDEX window, src/lib.cpp:272-340.  Not exact FPS: after one full min-update against the start point,
+// a pick only min-updates the points whose index lies within k/2 of it (the window is shifted, not shrunk, at the array
+// ends, lib.cpp:296-300), then the arg-max runs over ALL points with strict '>' from -1 (lowest index among equal maxima,
+// lib.cpp:311-315).  The reference pays O(n) per pick for that arg-max; here one CTA per cloud keeps the maximum of every
+// 256-point segment as a 64-bit key (distance bits, ~index) in shared memory, so a pick costs the window (w + 1 distances),
+// the few segments the window touches, and a reduction over n / 256 keys.  Distances in the reference's arithmetic
+// (individually rounded sub / mul / add in dimension order, common.cuh); the running distances live in global memory.
+#include "common.cuh"
+#include "engine.h"
+
+namespace fps {
+
+constexpr u32 NP_T = 256, NP_NW = NP_T / 32, NP_SEG = 256, NP_MAXDIM = 64;
+
+struct NpduArgs {
+    const float *pts;    // [B][n][dim]
+    float *dm;           // [B][npad] running distances
+    const u64 *starts;   // nullptr or [B]
+    u64 *out;            // [B][k]
+    u32 B, n, npad, dim, k, w;
+};
+
+__device__ __forceinline__ float np_sqdist(const float *p, const float *r, u32 dim) {
+    float t = __fsub_rn(p[0], r[0]);
+    float acc = __fmul_rn(t, t);
+    for (u32 j = 1; j < dim; ++j) {
+        t = __fsub_rn(p[j], r[j]);
+        acc = __fadd_rn(acc, __fmul_rn(t, t));
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(NP_T) npdu_kernel(NpduArgs a) {
+    extern __shared__ __align__(8) u64 segkey[];   // [ceil(n / NP_SEG)]
+    __shared__ u64 wred[NP_NW];
+    __shared__ float sref[NP_MAXDIM];
+    const u32 tid = threadIdx.x, lane = lane_id(), warp = warp_id();
+    const u32 n = a.n, dim = a.dim, nseg = (n + NP_SEG - 1) / NP_SEG;
+    for (u32 cloud = blockIdx.x; cloud < a.B; cloud += gridDim.x) {
+        const float *p = a.pts + (size_t)cloud * n * dim;
+        float *dm = a.dm + (size_t)cloud * a.npad;
+        u64 *out = a.out + (size_t)cloud * a.k;
+        u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;
+        __syncthreads();
+        if (tid < dim) sref[tid] = p[(size_t)cur * dim + tid];
+        __syncthreads();
+        for (u32 i = tid; i < n; i += NP_T) dm[i] = np_sqdist(p + (size_t)i * dim, sref, dim);   // min(+inf, d), lib.cpp:319-326
+        __syncthreads();
+        auto seg_key = [&](u32 sg) {   // one warp: the segment's largest distance, lowest index among equals
+            u64 best = 0;
+            const u32 i1 = min(n, (sg + 1) * NP_SEG);
+            for (u32 i = sg * NP_SEG + lane; i < i1; i += 32) {
+                const u64 key = make_key(dm[i], ~i);
+                best = key > best ? key : best;
+            }
+            best = warp_max_key(best);
+            if (lane == 0) segkey[sg] = best;
+        };
+        for (u32 sg = warp; sg < nseg; sg += NP_NW) seg_key(sg);
+        if (tid == 0) out[0] = cur;
+        const long long P = (long long)n, hw = (long long)(a.w / 2);
+        for (u32 t = 1; t < a.k; ++t) {
+            long long s = (long long)cur - hw, e = (long long)cur + hw;   // lib.cpp:294-300
+            if (s < 0) e -= s, s = 0;
+            if (e >= P) {
+                s = s - (e - P + 1);
+                if (s < 0) s = 0;
+                e = P - 1;
+            }
+            for (long long i = s + tid; i <= e; i += NP_T) {
+                const float v = np_sqdist(p + (size_t)i * dim, sref, dim);
+                if (v < dm[i]) dm[i] = v;
+            }
+            __syncthreads();
+            for (u32 sg = (u32)(s / NP_SEG) + warp; sg <= (u32)(e / NP_SEG); sg += NP_NW) seg_key(sg);
+            __syncthreads();
+            u64 best = 0;
+            for (u32 sg = tid; sg < nseg; sg += NP_T) best = segkey[sg] > best ? segkey[sg] : best;
+            best = warp_max_key(best);
+            if (lane == 0) wred[warp] = best;
+            __syncthreads();
+            best = wred[0];
+#pragma unroll
+            for (u32 wv = 1; wv < NP_NW; ++wv) best = wred[wv] > best ? wred[wv] : best;
+            cur = ~(u32)best;
+            if (tid == 0) out[t] = cur;
+            if (tid < dim) sref[tid] = p[(size_t)cur * dim + tid];
+            __syncthreads();
+        }
+    }
+}
+
+size_t npdu_workspace_bytes(size_t B, size_t n) { return B * ((n + 31) & ~(size_t)31) * sizeof(float) + 256; }
+
+cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t k, size_t w, const u64 *starts, u64 *out,
+                        void *ws, int n_sms, cudaStream_t st) {
+    if (dim == 0 || dim > NP_MAXDIM) return cudaErrorNotSupported;
+    const size_t smem = ((n + NP_SEG - 1) / NP_SEG) * sizeof(u64);
+    if (smem > 200 * 1024) return cudaErrorNotSupported;
+    NpduArgs a;
+    a.pts = pts;
+    a.dm = static_cast<float *>(ws);
+    a.starts = starts;
+    a.out = out;
+    a.B = (u32)B, a.n = (u32)n, a.npad = (u32)((n + 31) & ~(size_t)31), a.dim = (u32)dim, a.k = (u32)k;
+    a.w = (u32)(w > 0xffffffffull ? 0xffffffffull : w);
+    cudaError_t e = cudaFuncSetAttribute(npdu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    size_t grid = (size_t)n_sms * 8;
+    if (grid > B) grid = B;
+    npdu_kernel<<<(unsigned)grid, NP_T, smem, st>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace fps

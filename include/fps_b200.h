@@ -80,11 +80,22 @@ FPS_API int fps_b200_kdline_batch(const float *points, size_t B, size_t n, size_
 FPS_API int fps_b200_kdtree_batch(const float *points, size_t B, size_t n, size_t dim, size_t k,
                           const size_t *start, size_t *out_indices, const int *devices, int n_devices);
 
+/* FPS with the nearest-point-distance-updating heuristic over an index window (NOT exact FPS).  Replaces
+ * fps_npdu_sampling (src/lib.cpp:272-340), which the reference runs inline in its pybind function: after a full
+ * min-update against the start point, every pick min-updates only the points whose index lies within window / 2 of it
+ * (window shifted at the array ends) and the next pick is the arg-max over all points, lowest index among equals.
+ * Same indices as the reference for the same `window` (the python front-end's default is n / n_samples * 16). */
+FPS_API int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_samples, size_t window, size_t start_idx,
+                  size_t *out_indices);
+FPS_API int fps_b200_npdu_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t window,
+                        const size_t *start, size_t *out_indices, const int *devices, int n_devices);
+
 /* ---- batches, device pointers (inputs already resident in HBM) ---------------------------------- */
 
 #define FPS_ALGO_VANILLA 0
 #define FPS_ALGO_KDLINE 1
 #define FPS_ALGO_KDTREE 2
+#define FPS_ALGO_NPDU 3 /* host-pointer entries only */
 
 /* bytes of scratch the *_dev calls need on the current device for this shape (256-byte aligned base) */
 FPS_API size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t k, size_t height);

@@ -76,6 +76,42 @@ int oracle_fps_vanilla(const float *pts, size_t n, size_t d, size_t k, const siz
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * FPS with the nearest-point-distance-updating heuristic over an INDEX window (fps_npdu_sampling).
+ * Follows src/lib.cpp:272-340: a full min-update against the start point, then per pick a min-update of the
+ * points whose index lies within k/2 of the last pick (window shifted, not shrunk, at the array ends) and an
+ * arg-max over ALL points with strict '>' from -1 (lowest index among equal maxima).
+ * returns 0 ok, 2 bad start, 3 bad sizes.
+ * ------------------------------------------------------------------------------------------------ */
+int oracle_fps_npdu(const float *pts, size_t n, size_t d, size_t n_samples, size_t k, size_t start, size_t *out) {
+    if (n == 0 || d == 0 || n_samples == 0 || n_samples > n) return 3;
+    if (start >= n) return 2;
+    float *dm = (float *)malloc(n * sizeof(float));
+    if (!dm) return 3;
+    for (size_t i = 0; i < n; ++i) dm[i] = sqdist(pts + i * d, pts + start * d, d);   /* min(+inf, .) */
+    size_t cur = start;
+    out[0] = cur;
+    const long long P = (long long)n, hw = (long long)(k / 2);
+    for (size_t t = 1; t < n_samples; ++t) {
+        long long s = (long long)cur - hw, e = (long long)cur + hw;
+        if (s < 0) { e -= s; s = 0; }
+        if (e >= P) { s = s - (e - P + 1); if (s < 0) s = 0; e = P - 1; }
+        const float *q = pts + cur * d;
+        for (long long i = s; i <= e; ++i) {
+            float v = sqdist(pts + (size_t)i * d, q, d);
+            if (v < dm[i]) dm[i] = v;
+        }
+        float best = -1.0f;
+        size_t bi = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (dm[i] > best) { best = dm[i]; bi = i; }
+        cur = bi;
+        out[t] = cur;
+    }
+    free(dm);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * kd-line tree build.  Follows src/_ext/KDTreeBase.h:84-207 + src/_ext/KDLineTree.h:37-39,87-92.
  * Works on a permuted row copy q[n][d] and the permutation perm[n] (perm[pos] = original id).
  * Emits leaves in DFS-left-first order == ascending position order.

@@ -40,6 +40,8 @@ def _load():
         L.oracle_kdline_sample.argtypes = [fp, sz, sz, sz, sz, sz, szp, ctypes.c_void_p]
         L.oracle_kdline_sample_eager.argtypes = [fp, sz, sz, sz, sz, sz, szp]
         L.oracle_certify_fps.argtypes = [fp, sz, sz, sz, szp, sz, ctypes.c_int, ctypes.c_int, szp]
+        L.oracle_fps_npdu.argtypes = [fp, sz, sz, sz, sz, sz, szp]
+        L.oracle_fps_npdu.restype = ctypes.c_int
         for f in (L.oracle_fps_vanilla, L.oracle_kdline_build, L.oracle_kdline_sample,
                   L.oracle_kdline_sample_eager, L.oracle_certify_fps):
             f.restype = ctypes.c_int
@@ -66,6 +68,15 @@ def fps_vanilla(pc, k, start=0):
     rc = _load().oracle_fps_vanilla(pc.ctypes.data, pc.shape[0], pc.shape[1], k, starts.ctypes.data,
                                     starts.size, out.ctypes.data)
     _check(rc, "oracle_fps_vanilla")
+    return out
+
+
+def fps_npdu(pc, n_samples, w, start=0):
+    """Oracle twin of fpsample._fpsample._fps_npdu_sampling (index-window heuristic, src/lib.cpp:272-340)."""
+    pc = _f32(pc)
+    out = np.empty(n_samples, dtype=np.uint64)
+    rc = _load().oracle_fps_npdu(pc.ctypes.data, pc.shape[0], pc.shape[1], n_samples, w, start, out.ctypes.data)
+    _check(rc, "oracle_fps_npdu")
     return out
 
 

@@ -96,6 +96,18 @@ CASES = [
     *[(f"dim{d}_kdtree", ("uniform", 40 + d, 2000, d), "kdtree", dict(k=300, start=d)) for d in (1, 2, 4, 5, 7, 8)],
     ("n_odd_kdtree", ("uniform", 60, 4099, 3), "kdtree", dict(k=1000, start=4098)),
     ("k1_kdtree", ("uniform", 61, 100, 3), "kdtree", dict(k=1, start=42)),
+    # --- fps_npdu_sampling (index-window heuristic, src/lib.cpp:272-340); w = window ----
+    ("G0_npdu", ("rand42", 4096, 3), "npdu", dict(k=1024, w=64, start=0)),
+    ("cfg3_npdu", ("uniform", 2000, 16384, 3), "npdu", dict(k=4096, w=64, start=5)),
+    ("grid_d2_npdu", ("grid", 12, 3000, 2), "npdu", dict(k=500, w=10, start=7)),
+    ("grid_d1_npdu", ("grid", 11, 777, 1), "npdu", dict(k=300, w=33, start=776)),
+    ("wide_npdu", ("uniform", 70, 4099, 3), "npdu", dict(k=1000, w=2000, start=0)),
+    ("full_npdu", ("uniform", 71, 5000, 3), "npdu", dict(k=5000, w=4999, start=3)),
+    ("w1_npdu", ("uniform", 72, 2000, 6), "npdu", dict(k=300, w=1, start=5)),
+    ("w0_npdu", ("uniform", 73, 500, 3), "npdu", dict(k=100, w=0, start=499)),
+    ("lidar_npdu", ("lidar", 21, 20000), "npdu", dict(k=2048, w=156, start=11)),
+    ("dim12_npdu", ("uniform", 52, 2000, 12), "npdu", dict(k=300, w=100, start=12)),
+    ("dup_npdu", ("dup", 10, 3), "npdu", dict(k=5, w=4, start=2)),
 ]
 
 CASE_BY_ID = {c[0]: c for c in CASES}

@@ -33,6 +33,8 @@ def gpu_call(pc, call, p):
         return capi.vanilla(pc, p["k"], p["start"])
     if call == "kdtree":
         return capi.kdtree(pc, p["k"], p["start"])
+    if call == "npdu":
+        return capi.npdu(pc, p["k"], p["w"], p["start"])
     return capi.kdline(pc, p["k"], p["h"], p["start"])
 
 
@@ -409,6 +411,27 @@ def test_sequential_sum_tiles_are_bit_exact():
             assert got.tobytes() == want.tobytes(), f"{name} tile={tile}: {got!r} != {want!r}"
             some_fast += int(fast.cpu().numpy()[0])
     assert some_fast > 1000   # the scan path really ran
+
+
+def test_npdu_matches_the_oracle_and_the_front_end_is_a_drop_in(oracle, golden):
+    """fps_npdu_sampling: the index-window heuristic, bit-identical to src/lib.cpp:272-340"""
+    for n, d, k, w, s, gen in [(4096, 3, 1024, 64, 0, "u"), (3000, 2, 500, 10, 7, "g"), (20000, 3, 2048, 156, 11, "l"),
+                               (100000, 3, 4096, 390, 5, "u"), (777, 1, 300, 33, 776, "g"), (2000, 6, 300, 1, 5, "u"),
+                               (5000, 3, 5000, 4999, 3, "u"), (300, 3, 1, 8, 299, "u"), (257, 3, 257, 300, 0, "g")]:
+        pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d), "l": lambda: synth.lidar(n, n)}[gen]()
+        np.testing.assert_array_equal(capi.npdu(pc, k, w, s), oracle.fps_npdu(pc, k, w, s), err_msg=str((n, d, k, w, s, gen)))
+    pcs = synth.uniform_batch(4600, 300, 4096, 3)
+    st = (np.arange(300) * 13) % 4096
+    got = capi.npdu_batch(pcs, 512, 128, st, devices=[0])
+    for b in range(0, 300, 17):
+        np.testing.assert_array_equal(got[b], oracle.fps_npdu(pcs[b], 512, 128, int(st[b])))
+    np.random.seed(42)
+    pc = np.random.rand(4096, 3)
+    out = fps.fps_npdu_sampling(pc, 1024, start_idx=0)                 # default window: n / n_samples * 16 = 64
+    assert out.dtype == np.uint64 and out.shape == (1024,)
+    np.testing.assert_array_equal(out, golden["G0_npdu"])
+    with pytest.warns(UserWarning):
+        np.testing.assert_array_equal(fps.fps_npdu_sampling(pc, 100, w=10**6, start_idx=3), oracle.fps_npdu(pc, 100, 4095, 3))
 
 
 def test_device_pointer_entries(oracle):

@@ -132,9 +132,8 @@ def test_c_abi_return_codes_like_reference():
 
 
 def test_out_of_scope_entries_say_so():
-    for f in (fps.fps_npdu_sampling, fps.fps_npdu_kdtree_sampling):
-        with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
-            f(PC, 10)
+    with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
+        fps.fps_npdu_kdtree_sampling(PC, 10)   # needs nanoflann's kNN: the one reference entry that stays out of scope
 
 
 @pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU behaviour")
@@ -142,7 +141,8 @@ def test_no_cpu_fallback_without_gpu():
     assert capi.device_count() == 0
     for call in (lambda: fps.fps_sampling(PC, 10, 0), lambda: fps.bucket_fps_kdline_sampling(PC, 10, 3, 0),
                  lambda: fps.fps_sampling_batch(PC[None], 10), lambda: fps.bucket_fps_kdline_sampling_batch(PC[None], 10, 3),
-                 lambda: fps.bucket_fps_kdtree_sampling(PC, 10, 0), lambda: fps.bucket_fps_kdtree_sampling_batch(PC[None], 10)):
+                 lambda: fps.bucket_fps_kdtree_sampling(PC, 10, 0), lambda: fps.bucket_fps_kdtree_sampling_batch(PC[None], 10),
+                 lambda: fps.fps_npdu_sampling(PC, 10, 8, 0)):
         with pytest.raises(RuntimeError, match="error code 4"):   # FPS_ERR_NO_DEVICE
             call()
     assert "no CPU fallback" in capi.lib().fps_b200_last_error().decode()

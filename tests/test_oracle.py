@@ -24,6 +24,8 @@ def run_oracle(O, pc, call, p):
         return O.fps_vanilla(pc, p["k"], p["start"])
     if call == "kdtree":
         return O.kdtree(pc, p["k"], p["start"])
+    if call == "npdu":
+        return O.fps_npdu(pc, p["k"], p["w"], p["start"])
     return O.kdline(pc, p["k"], p["h"], p["start"])
 
 
