@@ -4,12 +4,16 @@ Same Python surface as the reference front-end (src/fpsample/__init__.py:35-65, 
 
     fps_sampling(pc, n_samples, start_idx=None)                      -> uint64[n_samples]
     bucket_fps_kdline_sampling(pc, n_samples, h, start_idx=None)     -> uint64[n_samples]
+    bucket_fps_kdtree_sampling(pc, n_samples, start_idx=None)        -> uint64[n_samples]   (:145-171)
+    fps_npdu_sampling(pc, n_samples, w=None, start_idx=None)         -> uint64[n_samples]   (:66-103)
 
-plus batched twins over [B, N, D] arrays (new):
+(fps_npdu_kdtree_sampling, which needs nanoflann's kNN, is the one entry that raises NotImplementedError) plus batched twins over [B, N, D] arrays (new):
 
     fps_sampling_batch(pcs, n_samples, start_idx=None, devices=None)               -> uint64[B, n_samples]
     bucket_fps_kdline_sampling_batch(pcs, n_samples, h, start_idx=None, devices=None)
+    bucket_fps_kdtree_sampling_batch(pcs, n_samples, start_idx=None, devices=None)
 
+Inputs may be numpy arrays or GPU-resident arrays (anything with __cuda_array_interface__: float32, C-contiguous).
 Everything runs on the GPU through the C ABI in include/fps_b200.h; there is no CPU fallback and the
 import fails loudly when the native extension has not been built (python build_native.py).
 """

@@ -5,7 +5,8 @@
 // lib.cpp:311-315).  The reference pays O(n) per pick for that arg-max; here one CTA per cloud keeps the maximum of every
 // 256-point segment as a 64-bit key (distance bits, ~index) in shared memory, so a pick costs the window (w + 1 distances),
 // the few segments the window touches, and a reduction over n / 256 keys.  Distances in the reference's arithmetic
-// (individually rounded sub / mul / add in dimension order, common.cuh); the running distances live in global memory.
+// (individually rounded sub / mul / add in dimension order, common.cuh); the running distances live in shared memory for
+// clouds of up to 16 384 points, in global memory (L2) beyond.
 #include "common.cuh"
 #include "engine.h"
 
@@ -19,6 +20,7 @@ struct NpduArgs {
     const u64 *starts;   // nullptr or [B]
     u64 *out;            // [B][k]
     u32 B, n, npad, dim, k, w;
+    u32 dm_smem;         // the running distances fit shared memory next to the segment keys (n <= 16 384)
 };
 
 __device__ __forceinline__ float np_sqdist(const float *p, const float *r, u32 dim) {
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(NP_T) npdu_kernel(NpduArgs a) {
     const u32 n = a.n, dim = a.dim, nseg = (n + NP_SEG - 1) / NP_SEG;
     for (u32 cloud = blockIdx.x; cloud < a.B; cloud += gridDim.x) {
         const float *p = a.pts + (size_t)cloud * n * dim;
-        float *dm = a.dm + (size_t)cloud * a.npad;
+        float *dm = a.dm_smem ? reinterpret_cast<float *>(segkey + nseg) : a.dm + (size_t)cloud * a.npad;
         u64 *out = a.out + (size_t)cloud * a.k;
         u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;
         __syncthreads();
@@ -96,8 +98,10 @@ size_t npdu_workspace_bytes(size_t B, size_t n) { return B * ((n + 31) & ~(size_
 cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t k, size_t w, const u64 *starts, u64 *out,
                         void *ws, int n_sms, cudaStream_t st) {
     if (dim == 0 || dim > NP_MAXDIM) return cudaErrorNotSupported;
-    const size_t smem = ((n + NP_SEG - 1) / NP_SEG) * sizeof(u64);
+    size_t smem = ((n + NP_SEG - 1) / NP_SEG) * sizeof(u64);
     if (smem > 200 * 1024) return cudaErrorNotSupported;
+    const bool dm_smem = n <= 16384;   // 64 KB of distances: still three or more clouds per SM
+    if (dm_smem) smem += n * sizeof(float);
     NpduArgs a;
     a.pts = pts;
     a.dm = static_cast<float *>(ws);
@@ -105,6 +109,7 @@ cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t
     a.out = out;
     a.B = (u32)B, a.n = (u32)n, a.npad = (u32)((n + 31) & ~(size_t)31), a.dim = (u32)dim, a.k = (u32)k;
     a.w = (u32)(w > 0xffffffffull ? 0xffffffffull : w);
+    a.dm_smem = dm_smem ? 1u : 0u;
     cudaError_t e = cudaFuncSetAttribute(npdu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     size_t grid = (size_t)n_sms * 8;
