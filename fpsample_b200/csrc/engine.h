@@ -16,6 +16,7 @@ struct VanillaArgs {
     u64 *out;           // [B][k]
     u32 n, dim, k, n_starts;
     u32 slice;          // points per CTA of a cluster
+    u64 negzero;        // two binary32 -0.0, set by launch_vanilla_cluster: an operand ptxas cannot see through (vanilla.cu)
 };
 
 struct VanillaPlan {

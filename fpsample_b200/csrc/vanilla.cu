@@ -36,6 +36,40 @@ struct VanillaSmem {
     XSlot xslot[2][MAXC];        // per-CTA candidates, double buffered
 };
 
+// ---- packed binary32 arithmetic (Blackwell add / sub / fma .f32x2 -> FADD2 / FFMA2): two points per instruction -------
+// Each half is an individually rounded IEEE operation, so the reference's arithmetic order is kept bit for bit.  ptxas
+// contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, so the product is written fma(t, t, -0.0)
+// with the -0.0 pair coming in as a kernel argument (opaque to the compiler): one rounding of t * t, adding -0 changes
+// nothing (+0 + -0 = +0), and an FMA result cannot be contracted into the following add.  scripts/micro/f32x2.cu.
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ u64 sq2(u64 t, u64 nz) {
+    u64 r;
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(t), "l"(nz));
+    return r;
+}
+template <int DIM>
+__device__ __forceinline__ u64 sqdist2(const u64 (&P)[DIM], const u64 (&Q)[DIM], u64 nz) {
+    u64 acc = sq2(sub2(P[0], Q[0]), nz);
+#pragma unroll
+    for (int j = 1; j < DIM; ++j) acc = add2(acc, sq2(sub2(P[j], Q[j]), nz));
+    return acc;
+}
+
 template <int DIM, int PPT>
 __global__ void __launch_bounds__(VT, (PPT * (DIM + 1) <= 36) ? 2 : 1)
 vanilla_cluster_kernel(VanillaArgs a) {
@@ -77,16 +111,20 @@ vanilla_cluster_kernel(VanillaArgs a) {
     if (C > 1) cluster_sync_all();  // every CTA's exchange mbarrier is initialised before remote arrives
 
     // ---- registers: my points and their running min distances ----------------------------------------
-    float p[PPT][DIM];
+    static_assert(PPT % 2 == 0, "points are held in pairs");
+    u64 P2[PPT / 2][DIM];   // points (2j, 2j + 1) of this thread, packed per dimension
     float dm[PPT];
 #pragma unroll
-    for (int j = 0; j < PPT; ++j) {
-        const u32 li = j * VT + tid;
-        const bool valid = li < cnt;
+    for (int j = 0; j < PPT; j += 2) {
+        const u32 l0 = j * VT + tid, l1 = (j + 1) * VT + tid;
+        const bool v0 = l0 < cnt, v1 = l1 < cnt;
 #pragma unroll
-        for (int c = 0; c < DIM; ++c) p[j][c] = (valid && c < dim) ? scoord[li * dim + c] : 0.0f;
-        dm[j] = valid ? __int_as_float(0x7f800000) : -1.0f;  // +inf (lib.cpp:206); -1 never wins
+        for (int c = 0; c < DIM; ++c)
+            P2[j / 2][c] = pk2((v0 && c < dim) ? scoord[l0 * dim + c] : 0.0f, (v1 && c < dim) ? scoord[l1 * dim + c] : 0.0f);
+        dm[j] = v0 ? __int_as_float(0x7f800000) : -1.0f;      // +inf (lib.cpp:206); -1 never wins
+        dm[j + 1] = v1 ? __int_as_float(0x7f800000) : -1.0f;
     }
+    const u64 nz = a.negzero;
 
     const u32 k = a.k, ns = a.n_starts;
     const u64 *starts = a.starts ? a.starts + (size_t)cloud * ns : nullptr;
@@ -103,15 +141,17 @@ vanilla_cluster_kernel(VanillaArgs a) {
         // min-update + thread-local argmax, ascending index order so '>=' keeps the highest index
         float best = -1.0f;
         u32 bj = 0;
+        u64 Q2[DIM];
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            float d = sqdist<DIM>(p[j], q);
-            float v = fminf(dm[j], d);
-            dm[j] = v;
-            if (v >= best) {
-                best = v;
-                bj = j;
-            }
+        for (int c = 0; c < DIM; ++c) Q2[c] = pk2(q[c], q[c]);
+#pragma unroll
+        for (int j = 0; j < PPT; j += 2) {
+            float d0, d1;
+            up2(sqdist2<DIM>(P2[j / 2], Q2, nz), d0, d1);
+            const float v0 = fminf(dm[j], d0), v1 = fminf(dm[j + 1], d1);
+            dm[j] = v0, dm[j + 1] = v1;
+            if (v0 >= best) best = v0, bj = j;
+            if (v1 >= best) best = v1, bj = j + 1;
         }
         u64 key = (best < 0.0f) ? 0ull : make_key(best, lo + bj * VT + tid);
         key = warp_max_key(key);
@@ -334,6 +374,7 @@ bool plan_vanilla_cluster(size_t n, size_t dim, size_t B, int n_sms, VanillaPlan
 }
 
 cudaError_t launch_vanilla_cluster(const VanillaPlan &pl, VanillaArgs a, u32 B, cudaStream_t st) {
+    a.negzero = 0x8000000080000000ull;
     a.slice = pl.slice;
     switch (pl.dimp) {
         case 2: return dispatch_ppt<2>(pl.ppt, a, B, pl.C, pl.smem, st);
