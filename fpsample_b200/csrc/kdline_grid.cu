@@ -67,6 +67,7 @@ struct GridArgs {
     const float *qv;     // IDS: per cloud [dim][npad] coordinates by virtual position (the input reversed, SoA)
     size_t qv_stride;    // floats
     u32 n_starts;        // IDS: forced first picks per cloud (original indices), >= 1
+    u64 negzero;         // two binary32 -0.0 as an operand the compiler cannot see through (packed products, common.cuh)
 };
 
 // gpu-scope relaxed accesses: served by L2, never by a stale L1 line
@@ -387,27 +388,28 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) x[c] = pts[(size_t)c * PCQ + slot];
                         float4 v = pv[slot];
+                        u64 X01[DIM], X23[DIM];   // the four points of this slot, two per packed operand (FADD2 / FFMA2)
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) X01[c] = pk2(x[c].x, x[c].y), X23[c] = pk2(x[c].z, x[c].w);
                         u32 m = mask;
 #pragma unroll 1
                         while (m) {
                             const u32 j = __ffs(m) - 1;
                             m &= m - 1;
                             const u32 rj = __shfl_sync(FULL, ri, j);
-                            float rc[DIM];
-#pragma unroll
-                            for (int c = 0; c < DIM; ++c) rc[c] = tc[c * G_ECAP + rj];
-                            float p0[DIM], p1[DIM], p2[DIM], p3[DIM];
+                            u64 RC[DIM];
 #pragma unroll
                             for (int c = 0; c < DIM; ++c) {
-                                p0[c] = x[c].x;
-                                p1[c] = x[c].y;
-                                p2[c] = x[c].z;
-                                p3[c] = x[c].w;
+                                const float r = tc[c * G_ECAP + rj];
+                                RC[c] = pk2(r, r);
                             }
-                            v.x = fminf(v.x, sqdist<DIM>(p0, rc));   // std::min(dis, d), Point.h:82-86
-                            v.y = fminf(v.y, sqdist<DIM>(p1, rc));
-                            v.z = fminf(v.z, sqdist<DIM>(p2, rc));
-                            v.w = fminf(v.w, sqdist<DIM>(p3, rc));
+                            float d0, d1, d2, d3;
+                            up2(sqdist2<DIM>(X01, RC, a.negzero), d0, d1);
+                            up2(sqdist2<DIM>(X23, RC, a.negzero), d2, d3);
+                            v.x = fminf(v.x, d0);   // std::min(dis, d), Point.h:82-86
+                            v.y = fminf(v.y, d1);
+                            v.z = fminf(v.z, d2);
+                            v.w = fminf(v.w, d3);
                         }
                         pv[slot] = v;
                     }
@@ -941,6 +943,7 @@ cudaError_t launch_kdline_grid(const GridPlan &pl, unsigned char *region, size_t
                                unsigned char *pub, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st, const float *pts_vanilla,
                                float *qv, u32 n_starts) {
     GridArgs a;
+    a.negzero = 0x8000000080000000ull;
     a.S = 1u << h;
     a.region = region;
     a.region_stride = region_stride;

@@ -36,40 +36,6 @@ struct VanillaSmem {
     XSlot xslot[2][MAXC];        // per-CTA candidates, double buffered
 };
 
-// ---- packed binary32 arithmetic (Blackwell add / sub / fma .f32x2 -> FADD2 / FFMA2): two points per instruction -------
-// Each half is an individually rounded IEEE operation, so the reference's arithmetic order is kept bit for bit.  ptxas
-// contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, so the product is written fma(t, t, -0.0)
-// with the -0.0 pair coming in as a kernel argument (opaque to the compiler): one rounding of t * t, adding -0 changes
-// nothing (+0 + -0 = +0), and an FMA result cannot be contracted into the following add.  scripts/micro/f32x2.cu.
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void up2(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 sub2(u64 a, u64 b) {
-    u64 r;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b) {
-    u64 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ u64 sq2(u64 t, u64 nz) {
-    u64 r;
-    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(t), "l"(nz));
-    return r;
-}
-template <int DIM>
-__device__ __forceinline__ u64 sqdist2(const u64 (&P)[DIM], const u64 (&Q)[DIM], u64 nz) {
-    u64 acc = sq2(sub2(P[0], Q[0]), nz);
-#pragma unroll
-    for (int j = 1; j < DIM; ++j) acc = add2(acc, sq2(sub2(P[j], Q[j]), nz));
-    return acc;
-}
-
 template <int DIM, int PPT>
 __global__ void __launch_bounds__(VT, (PPT * (DIM + 1) <= 36) ? 2 : 1)
 vanilla_cluster_kernel(VanillaArgs a) {
