@@ -45,6 +45,7 @@ struct WarpArgs {
     u32 B, n, npad, dim, k, S, nlo_pad;
     u32 nch;            // chunks per cloud, padded to a multiple of W_U
     u32 n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, R, lazy, hybrid;
+    u64 negzero;        // two binary32 -0.0 as an operand the compiler cannot see through (packed products, common.cuh)
 };
 
 __device__ __forceinline__ float4 lds128(u32 a) {
@@ -390,15 +391,33 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                     float w[8];
                     w[0] = f0.x, w[1] = f0.y, w[2] = f0.z, w[3] = f0.w;
                     if constexpr (DIM > 4) w[4] = f1.x, w[5] = f1.y, w[6] = f1.z, w[7] = f1.w;
-                    float ref[DIM];
+                    if constexpr (ST::kCoordsInPlace) {
+                        // global store (8 warps per SM, registers to spare): two chunks per FADD2 / FFMA2 (U is even);
+                        // on the on-chip stores the packed form costs the registers the 7-warp CTA does not have
+                        u64 RC[DIM];   // the sample, broadcast into both halves of a packed operand
 #pragma unroll
-                    for (int c = 0; c < DIM; ++c) ref[c] = w[c];
+                        for (int c = 0; c < DIM; ++c) RC[c] = pk2(w[c], w[c]);
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        float pt[DIM];
+                        for (int u = 0; u < U; u += 2) {
+                            u64 PT[DIM];
 #pragma unroll
-                        for (int c = 0; c < DIM; ++c) pt[c] = x[c][u];
-                        v[u] = fminf(v[u], sqdist<DIM>(pt, ref));   // std::min(dis, d), Point.h:82-86
+                            for (int c = 0; c < DIM; ++c) PT[c] = pk2(x[c][u], x[c][u + 1]);
+                            float d0, d1;
+                            up2(sqdist2<DIM>(PT, RC, a.negzero), d0, d1);
+                            v[u] = fminf(v[u], d0);   // std::min(dis, d), Point.h:82-86
+                            v[u + 1] = fminf(v[u + 1], d1);
+                        }
+                    } else {
+                        float ref[DIM];
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) ref[c] = w[c];
+#pragma unroll
+                        for (int u = 0; u < U; ++u) {
+                            float pt[DIM];
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) pt[c] = x[c][u];
+                            v[u] = fminf(v[u], sqdist<DIM>(pt, ref));   // std::min(dis, d), Point.h:82-86
+                        }
                     }
                 }
                 // positions outside [lo, hi) belong to a neighbour bucket (or are padding): they keep their value
@@ -756,6 +775,7 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     a.R = pl.rs;
     a.lazy = pl.lazy;
     a.hybrid = pl.hybrid;
+    a.negzero = 0x8000000080000000ull;
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;
