@@ -213,6 +213,22 @@ def gpu_arm(args):
         raise SystemExit("bench.py: no sm_100 device visible; there is no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1 and not os.environ.get("FPS_BENCH_NO_AFFINITY"):
+        # one process per GPU: run on (and first-touch the pinned buffers from) the cores next to this rank's GPU, so the
+        # eight concurrent uploads of an 8-GPU run do not all cross one socket's memory system
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = f"{len(cpus)} cores next to GPU {local}"
+        except Exception as e:   # affinity is an optimisation of the host side only
+            numa = f"unavailable ({type(e).__name__})"
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -340,7 +356,8 @@ def gpu_arm(args):
                                    f"start_idx=0, {B} clouds per GPU, seeds {seed}+i",
                        "clouds_per_gpu": B, "n": n, "d": d, "k": k, "h": h if algo == "kdline" else None, "algo": algo,
                        "l2": "inputs (%.0f MB/GPU) < L2: 256 MiB flush write between timed steps, outside the per-step CUDA-event pairs" % (B * n * d * 4 / 1e6),
-                       "plan": plan, "parallelism": f"dp{world} (independent clouds, contiguous shards, no data-path collective)"},
+                       "plan": plan, "parallelism": f"dp{world} (independent clouds, contiguous shards, no data-path collective)",
+                       **({"host_affinity": numa} if numa else {})},
             "e2e": {"value": e2e_value, "unit": "clouds/s", "h2d_bytes_per_step": B * n * d * 4,
                     "d2h_bytes_per_step": B * k * 8, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "fpsample_b200.%s(host ndarray) -> host ndarray" % ("fps_sampling_batch" if algo == "vanilla" else "bucket_fps_kdline_sampling_batch"),
