@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-fmad=false", *os.environ.get("FPS_NVCC_EXTRA", "").split(),  # bit-exact parity: no FMA contraction anywhere (the kernels also use *_rn)
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
-CU = ["vanilla.cu", "kdtree.cu", "kdline.cu", "kdsmall.cu", "seqsum.cu", "npdu.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_dist.cu", "kdline_grid.cu", "kdbuild.cu", "capi.cu"]
+CU = ["vanilla.cu", "kdtree.cu", "kdline.cu", "kdsmall.cu", "seqsum.cu", "npdu.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_stream.cu", "kdline_grid.cu", "kdbuild.cu", "comm.cu", "capi.cu"]
 HDR = ["common.cuh", "kdcommon.cuh", "seqsum.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
 
 
@@ -40,18 +40,21 @@ def build(force: bool = False, verbose: bool = False) -> None:
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)
     hdrs = [h if os.path.isabs(h) else os.path.join(CSRC, h) for h in HDR]
-    objs = []
+    objs, jobs = [], []
     for cu in CU:
         src = os.path.join(CSRC, cu)
         obj = os.path.join(objdir, cu.replace(".cu", ".o"))
         objs.append(obj)
         if force or _newer(obj, [src] + hdrs):
-            cmd = [NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj]
-            subprocess.check_call(cmd)
+            jobs.append([NVCC] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj])
+    if jobs:   # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as ex:
+            list(ex.map(subprocess.check_call, jobs))
     if force or _newer(LIB, objs):
         # default (static) cudart: the library does not depend on which libcudart the host process loaded
         subprocess.check_call([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs +
-                              ["-Xcompiler", "-fPIC"])
+                              ["-Xcompiler", "-fPIC", "-ldl"])
     src = os.path.join(CSRC, "pymodule.cpp")
     if force or _newer(EXT, [src, LIB] + hdrs):
         import pybind11

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfps_b200.so")
+LIB_PATH = os.environ.get("FPS_B200_LIB") or os.path.join(_HERE, "libfps_b200.so")   # FPS_B200_LIB: an experimental build (scripts/build_variant.sh)
 
 ALGO_VANILLA, ALGO_KDLINE, ALGO_KDTREE = 0, 1, 2
 
@@ -34,7 +34,18 @@ EXPORTS = {
     "fps_b200_last_error": (ctypes.c_char_p, []),
     "fps_b200_last_plan": (ctypes.c_char_p, []),
     "fps_b200_kernel_launches": (ctypes.c_uint64, []),
-    "fps_b200_debug_counters": (ctypes.c_int, [ctypes.c_void_p]),
+    "fps_b200_debug_counters": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
+    "fps_b200_comm_unique_id": (ctypes.c_int, [ctypes.c_void_p]),
+    "fps_b200_comm_init": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]),
+    "fps_b200_comm_init_local": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "fps_b200_comm_destroy": (None, []),
+    "fps_b200_comm_ranks": (ctypes.c_int, []),
+    "fps_b200_nccl_version": (ctypes.c_int, []),
+    "fps_b200_kdline_batch_sharded": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "fps_b200_vanilla_batch_sharded": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p]),
+    "fps_b200_gather_indices": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 3 + [ctypes.c_void_p]),
+    "fps_b200_set_tuning": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_long]),
+    "fps_b200_set_producer_stream": (None, [ctypes.c_void_p]),
     "fps_b200_phase_timing": (None, [ctypes.c_int]),
     "fps_b200_last_phase_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
@@ -78,13 +89,45 @@ def kernel_launches() -> int:
     return int(lib().fps_b200_kernel_launches())
 
 
-def debug_counters():
-    """phase counters of the last kd-line cluster launch: dict (diagnostics only)."""
+DBG_ASYNC, DBG_WARP, DBG_BUILD, DBG_GRID, DBG_STREAM = 0, 1, 2, 3, 4
+
+
+def debug_counters(which: int = DBG_ASYNC):
+    """16 raw counters of the last launch of one sampler family (diagnostics / bench.py's executed-work roofline)."""
     out = np.zeros(16, dtype=np.uint64)
-    _check("fps_b200_debug_counters", lib().fps_b200_debug_counters(out.ctypes.data))
+    _check("fps_b200_debug_counters", lib().fps_b200_debug_counters(which, out.ctypes.data))
+    if which != DBG_ASYNC:
+        return out
     names = ("iterations", "picks", "stalled_iterations", "cyc_poll_warptop", "cyc_wait_warps", "cyc_blocktop",
              "cyc_tests")
     return {k: int(v) for k, v in zip(names, out)}
+
+
+def set_tuning(name: str, value: int = -1) -> None:
+    """Planner override (value -1 = the planner's own choice); the environment is only read once, at first use."""
+    _check("fps_b200_set_tuning", lib().fps_b200_set_tuning(name.upper().encode(), int(value)))
+
+
+class tuning:
+    """`with capi.tuning(group=0, warp_global_minb=1): ...` -- overrides for the block, planner defaults afterwards."""
+
+    def __init__(self, **knobs):
+        self.knobs = knobs
+
+    def __enter__(self):
+        for k, v in self.knobs.items():
+            set_tuning(k, v)
+        return self
+
+    def __exit__(self, *exc):
+        for k in self.knobs:
+            set_tuning(k, -1)
+        return False
+
+
+def set_producer_stream(stream: int) -> None:
+    """The calling thread's next host-pointer-entry call with a DEVICE input waits for `stream` (a cudaStream_t) on the device."""
+    lib().fps_b200_set_producer_stream(stream or None)
 
 
 def phase_timing(enable: bool) -> None:
@@ -192,6 +235,68 @@ def kdtree_batch(pcs, k, start=None, devices=None):
     _check("fps_b200_kdtree_batch", lib().fps_b200_kdtree_batch(
         pcs.ctypes.data, b, n, d, k, None if st is None else st.ctypes.data, out.ctypes.data,
         None if dv is None else dv.ctypes.data, 0 if dv is None else dv.size))
+    return out
+
+
+# ---- multi-GPU: NCCL gather of the index arrays to rank 0 (include/fps_b200.h, csrc/comm.cu) ---------------------------------
+def comm_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    _check("fps_b200_comm_unique_id", lib().fps_b200_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(uid: bytes, n_ranks: int, rank: int) -> None:
+    assert len(uid) == 128
+    _check("fps_b200_comm_init", lib().fps_b200_comm_init(ctypes.create_string_buffer(uid, 128), n_ranks, rank))
+
+
+def comm_init_local(devices) -> None:
+    dv = np.asarray(devices, dtype=np.int32)
+    _check("fps_b200_comm_init_local", lib().fps_b200_comm_init_local(dv.ctypes.data, dv.size))
+
+
+def comm_destroy() -> None:
+    lib().fps_b200_comm_destroy()
+
+
+def comm_ranks() -> int:
+    return int(lib().fps_b200_comm_ranks())
+
+
+def nccl_version() -> int:
+    return int(lib().fps_b200_nccl_version())
+
+
+def _sharded(fn, name, pcs, n_clouds, k, start, is_root, *extra):
+    """pcs: this rank's shard (one process per GPU) or the whole batch (comm_init_local); numpy array or an int device address
+    with `shape`.  -> [n_clouds, k] uint64 where rank 0 lives (pinned), else None."""
+    if isinstance(pcs, tuple):
+        ptr, (b, n, d) = pcs
+        keep = None
+    else:
+        keep = pcs = _f32(pcs, 3)
+        ptr, (b, n, d) = pcs.ctypes.data, pcs.shape
+    st = _starts(start, b)
+    out = pinned_empty((n_clouds, k), np.uint64) if is_root else None
+    args = [ptr, n_clouds, n, d, k, None if st is None else st.ctypes.data] + list(extra) + [None if out is None else out.ctypes.data]
+    _check(name, fn(*args))
+    del keep
+    return out
+
+
+def kdline_batch_sharded(pcs, n_clouds, k, h, start=None, is_root=True):
+    return _sharded(lib().fps_b200_kdline_batch_sharded, "fps_b200_kdline_batch_sharded", pcs, n_clouds, k, start, is_root, h)
+
+
+def vanilla_batch_sharded(pcs, n_clouds, k, start=None, is_root=True):
+    return _sharded(lib().fps_b200_vanilla_batch_sharded, "fps_b200_vanilla_batch_sharded", pcs, n_clouds, k, start, is_root)
+
+
+def gather_indices(local, n_clouds, is_root=True):
+    local = np.ascontiguousarray(local, dtype=np.uint64)
+    nb, k = local.shape
+    out = pinned_empty((n_clouds, k), np.uint64) if is_root else None
+    _check("fps_b200_gather_indices", lib().fps_b200_gather_indices(local.ctypes.data, nb, k, n_clouds, None if out is None else out.ctypes.data))
     return out
 
 

@@ -15,6 +15,12 @@
 
 namespace fps {
 cudaError_t kb_debug_counters(unsigned long long *out16);
+// comm.cu
+int comm_gather(const u64 *const *locals, const cudaStream_t *after, size_t k, size_t n_clouds, u64 *out_rank0);
+int comm_world();
+int comm_local_endpoints();
+int comm_endpoint_device(int i);
+int comm_endpoint_rank(int i);
 
 static std::atomic<uint64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
@@ -23,6 +29,12 @@ static thread_local char tl_err[512] = "";
 static thread_local char tl_plan[512] = "";
 
 static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
+    va_end(ap);
+}
+void comm_set_err(const char *fmt, ...) {   // comm.cu reports through the same thread-local text
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(tl_err, sizeof(tl_err), fmt, ap);
@@ -43,6 +55,57 @@ static void set_plan(const char *fmt, ...) {
             return FPS_ERR_CUDA + (int)e__;                                                   \
         }                                                                                     \
     } while (0)
+
+// ---- tuning knobs: the environment is read ONCE, the call path reads this struct ------------------------------------------
+static Tuning g_tuning;
+static std::once_flag g_tuning_once;
+struct KnobDesc {
+    const char *name;
+    long Tuning::*lf;
+    int Tuning::*f;
+};
+static const KnobDesc kKnobs[] = {
+    {"GRID", nullptr, &Tuning::grid},           {"GROUP", nullptr, &Tuning::group},
+    {"GRIDBUILD", nullptr, &Tuning::gridbuild}, {"VANILLA_KD", nullptr, &Tuning::vanilla_kd},
+    {"PIPE", nullptr, &Tuning::pipe},           {"ZEROCOPY", nullptr, &Tuning::zerocopy},
+    {"GRID_ECAP", nullptr, &Tuning::grid_ecap}, {"WARP", nullptr, &Tuning::warp},
+    {"WARP_TMEM", nullptr, &Tuning::warp_tmem}, {"WARP_LAZY", nullptr, &Tuning::warp_lazy},
+    {"WARP_HYBRID", nullptr, &Tuning::warp_hybrid}, {"WARP_GLOBAL_MINB", &Tuning::warp_global_minb, nullptr},
+    {"KDSMALL", nullptr, &Tuning::kdsmall},     {"STREAM_WARPS", nullptr, &Tuning::stream_warps},
+    {"COUNT", nullptr, &Tuning::count},
+};
+static bool set_knob(const char *name, long v) {
+    for (const KnobDesc &k : kKnobs)
+        if (!strcmp(k.name, name)) {
+            if (k.lf) g_tuning.*(k.lf) = v;
+            else g_tuning.*(k.f) = (int)v;
+            return true;
+        }
+    return false;
+}
+const Tuning &tuning() {
+    std::call_once(g_tuning_once, [] {
+        for (const KnobDesc &k : kKnobs) {
+            const std::string env = std::string("FPS_B200_") + k.name;
+            if (const char *e = getenv(env.c_str())) set_knob(k.name, atol(e));
+        }
+    });
+    return g_tuning;
+}
+
+// ---- the caller's current device is restored on every exit path -----------------------------------------------------
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
 
 // ---- optional phase timing of the *_dev entries (bench.py: the dominant kernel's own duration) -----------------------
 // When enabled, the calling thread's next *_dev call records CUDA events on ITS stream around the build and the
@@ -89,7 +152,9 @@ struct DevCtx {
     int dev = -1, n_sms = 0;
     std::mutex mu;
     Lane lane[2];
+    Buf gout;                 // indices kept on the device for the NCCL gather (sharded entries)
     cudaEvent_t ev[8] = {};   // upload-chunk-landed events of the pipelined kd-line path
+    cudaEvent_t ev_in = nullptr;   // 'device-resident input is ready' (recorded on the producer's stream)
     bool ready = false;
 };
 
@@ -249,96 +314,122 @@ static int enqueue_vanilla(const float *d_pts, size_t B, size_t n, size_t dim, s
     return FPS_OK;
 }
 
+// ---- the kd-line route table -------------------------------------------------------------------------------------------
+// Which kernel builds the per-cloud regions and which one samples them.  The thresholds were measured on one B200 (the
+// script behind each is named); every decision can be overridden through fps_b200_set_tuning / FPS_B200_<KNOB>.
+//
+//   sampler       | takes                                                             | builder
+//   --------------+-------------------------------------------------------------------+--------------------------------------
+//   WarpOnChip    | cloud fits a shared-memory / TMEM slot, 2^h <= 128                | Small (kdsmall_kernel)
+//   Grid (groups) | n >= kGroupMinPoints and 1..8 CTAs hold a cloud, unless WarpStream | Small if the coordinates fit one SM, else
+//   Grid (whole)  | 1-4 clouds of >= 131 072 points that fit the SMs' shared memory   |   GridWide for few / huge / L2-bound
+//   WarpStream    | cloud not on chip, batch >= kStreamMinCloudsPerSm clouds per SM   |   batches, else PerCloud (kdline_kernel)
+//   AsyncCluster  | what is left of the clouds beyond one SM                          |
+//   FusedCta      | everything else (one CTA builds and samples, any h)               | Fused
+namespace route {
+constexpr size_t kGroupMinPoints = 8192;        // groups of CTAs with batched picks beat one warp per cloud from here (scripts/cmp_group.py)
+constexpr u32 kStreamGroupCtas = 8;             // a cloud that would tie up >= 8 CTAs of a group ...
+constexpr size_t kStreamMinCloudsPerSm = 2;     //   ... streams from HBM once the batch stacks 2 clouds per SM (scripts/cmp_cfg5.py:
+                                                //   16-CTA groups sample 4.7 k 100 k-point clouds/s at any batch size, the streaming kernel overtakes at ~300)
+constexpr size_t kStreamMinCloudsPerSmMid = 4;  //   3..7 CTAs per cloud: from 4 clouds per SM
+constexpr size_t kGridBuildMinPoints = 262144;  // one grid-wide launch per phase per level from here, whatever the batch (scripts/cmp_build5.py)
+}  // namespace route
+
+enum class Sampler { BuildOnly, WarpOnChip, WarpStream, Grid, AsyncCluster, FusedCta };
+enum class Builder { Small, GridWide, PerCloud, Fused };
+
 struct KdLayout {
     KdlinePlan pl;
     AsyncPlan ap;
     WarpPlan wp;
-    DistPlan dp;
+    StreamPlan stp;
     GridPlan gp;
     KdSmallPlan sp;
-    bool async, gridbuild, warp, dist, grid, small;
+    Sampler sampler;
+    Builder builder;
     size_t region_off, region_stride, aux_off, counter_off, pub_off, qv_off, total;
 };
 
-// fused single-CTA kernel when the cloud fits one SM's shared memory; otherwise build into per-cloud regions
-// and sample with the cluster coordinator/worker kernel
-static size_t tmp_stream_minB(int n_sms) { return (size_t)2 * n_sms; }
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
 static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms, bool build_only, KdLayout *L, bool ids = false) {
     cudaError_t e = plan_kdline(n, dim, h, B, n_sms, &L->pl);
     if (e != cudaSuccess) return e;
+    const Tuning &tu = tuning();
     L->region_off = L->region_stride = L->aux_off = L->counter_off = L->pub_off = L->qv_off = 0;
-    L->gridbuild = L->grid = L->dist = L->async = L->small = false;
     L->total = L->pl.ws_bytes;
-    // clouds that fit on chip: build into per-cloud regions, then one warp per cloud (records in smem / TMEM)
-    bool force_grid = false;   // tests force the whole-GPU sampler onto clouds the planner would keep on one SM
-    if (const char *e = getenv("FPS_B200_GRID")) force_grid = atoi(e) == 1;
-    if (const char *e = getenv("FPS_B200_GROUP")) force_grid = force_grid || atoi(e) == 1;
-    // medium clouds (>= 8192 points): groups of CTAs with batched picks beat one warp per cloud (1-3 clouds per SM)
-    bool prefer_group = false;
-    if (!build_only && !force_grid && n >= 8192) {
-        GridPlan tmp;
-        // ... unless the batch is big enough for the one-warp-per-cloud streaming kernel (>= 4 clouds per SM in flight,
-        // HBM-bound: BASELINE.json cfg 5) and a cloud would tie up 4 or more SMs
-        // (measured on 100 k-point clouds, scripts/cmp_cfg5.py: 16 CTAs per cloud sample 4.7 k clouds/s at any batch size, the
-        // streaming kernel needs ~55 ms however few clouds it gets -- it wins from ~2 clouds per SM: 300 clouds 5.0 k/s, 512 clouds 7.7 k/s)
-        const size_t stream_from = tmp_stream_minB(n_sms);
-        prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp, ids) && tmp.flat &&
-                       (ids || tmp.gc <= 2 || B < (tmp.gc >= 8 ? stream_from : (size_t)4 * n_sms));
-    }
-    if (build_only && plan_kdsmall(n, dim, h, B, n_sms, &L->sp)) {   // the build-only entry runs the kernel the samplers are fed by
-        L->small = true;
-        L->warp = false;
-        L->region_off = ((L->pl.ws_bytes > L->sp.ws_bytes ? L->pl.ws_bytes : L->sp.ws_bytes) + 255) & ~(size_t)255;
-        L->region_stride = kd_region_bytes(n, dim, h);
-        L->total = L->region_off + B * L->region_stride;
-        return cudaSuccess;
-    }
-    L->warp = !build_only && !force_grid && !prefer_group && !ids && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp);
-    if (L->warp) {
-        L->async = false;
-        L->small = plan_kdsmall(n, dim, h, B, n_sms, &L->sp);   // the build that feeds the regions
-        L->region_off = (((L->small && L->sp.ws_bytes > L->pl.ws_bytes) ? L->sp.ws_bytes : L->pl.ws_bytes) + 255) & ~(size_t)255;
-        L->region_stride = kd_region_bytes(n, dim, h);
-        L->counter_off = L->region_off + B * L->region_stride;
-        L->total = L->counter_off + 256;
-        // clouds that stay in global memory: the grid-wide per-level launches build a batch faster than one CTA per
-        // cloud working out of L2 (scripts/cmp_build5.py)
-        L->gridbuild = !L->small && L->wp.global;
-        if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = !L->small && atoi(e) != 0;
-        if (L->gridbuild) {
-            L->aux_off = (L->total + 255) & ~(size_t)255;
-            L->total = L->aux_off + B * kd_gridbuild_aux_bytes(n, dim, h);
+    L->sampler = Sampler::FusedCta;
+    L->builder = Builder::Fused;
+    const bool cloud_in_one_sm = (L->pl.in_smem & 1) != 0;
+
+    // ---- the sampler ----------------------------------------------------------------------------------------------
+    bool have_small = false;
+    if (build_only) {
+        L->sampler = Sampler::BuildOnly;
+        have_small = plan_kdsmall(n, dim, h, B, n_sms, &L->sp);   // the build-only entry runs the kernel the samplers are fed by
+        if (!have_small) return cudaSuccess;                      // ... or the fused kernel's build phase
+    } else {
+        const bool force_grid = tu.grid == 1 || tu.group == 1;    // tests force the grid sampler onto clouds the planner would keep on one SM
+        bool prefer_group = false;
+        if (!force_grid && n >= route::kGroupMinPoints) {
+            GridPlan tmp;
+            const size_t stream_from = route::kStreamMinCloudsPerSm * (size_t)n_sms;
+            prefer_group = plan_kdline_grid(n, dim, h, B, n_sms, &tmp, ids) && tmp.flat &&
+                           (ids || tmp.gc <= 2 ||
+                            B < (tmp.gc >= route::kStreamGroupCtas ? stream_from : route::kStreamMinCloudsPerSmMid * (size_t)n_sms));
         }
-        return cudaSuccess;
+        // not on chip: the points stay in global memory, a team of warps per cloud -- worth it only when the batch keeps every SM
+        // busy with clouds (throughput from clouds in flight, HBM-bound); small batches go to the cluster / grid kernels
+        const size_t stream_minB = tu.warp_global_minb >= 0 ? (size_t)tu.warp_global_minb : route::kStreamMinCloudsPerSm * (size_t)n_sms;
+        const bool warp_ok = !force_grid && !prefer_group && !ids && tu.warp != 0;
+        if (warp_ok && plan_kdline_warp(n, dim, h, B, n_sms, &L->wp))
+            L->sampler = Sampler::WarpOnChip;
+        else if (warp_ok && B >= stream_minB && plan_kdline_stream(n, dim, h, B, n_sms, &L->stp))
+            L->sampler = Sampler::WarpStream;
+        else if ((force_grid || prefer_group || ids || !cloud_in_one_sm) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp, ids))
+            L->sampler = Sampler::Grid;
+        else if (ids)
+            return cudaErrorNotSupported;
+        else if (!cloud_in_one_sm && plan_kdline_async(n, dim, h, B, n_sms, &L->ap))
+            L->sampler = Sampler::AsyncCluster;
+        else
+            return cudaSuccess;   // FusedCta
     }
-    // bigger clouds: buckets distributed over a cluster (kdline_dist.cu); the coordinator/worker kernel
-    // (kdline_async.cu) covers what is left (2^h > 512 buckets)
-    // one huge cloud: the whole GPU samples it, points in shared memory, batched picks (kdline_grid.cu)
-    L->grid = !build_only && (force_grid || prefer_group || ids || !(L->pl.in_smem & 1)) && plan_kdline_grid(n, dim, h, B, n_sms, &L->gp, ids);
-    if (ids && !L->grid) return cudaErrorNotSupported;
-    L->dist = !build_only && !L->grid && plan_kdline_dist(n, dim, h, B, n_sms, &L->dp);
-    L->async = !build_only && !L->grid && !L->dist && !(L->pl.in_smem & 1) && plan_kdline_async(n, dim, h, B, n_sms, &L->ap);
-    if (L->async || L->dist || L->grid) {
-        // few clouds: one CTA per cloud would idle most SMs during the build -> one grid-wide pass per tree level
-        // ... and so is any batch of clouds the per-cloud kernel would have to work on out of L2 (100 k-point clouds:
-        // 128 clouds 2.9 -> 2.1 ms, 512 clouds 10.9 -> 6.4 ms, scripts/cmp_build5.py)
-        L->gridbuild = B * 2 <= (size_t)n_sms || n >= 262144 || !(L->pl.in_smem & 1);
-        if (const char *e = getenv("FPS_B200_GRIDBUILD")) L->gridbuild = atoi(e) != 0;
-        // a cloud whose coordinates fit one SM's shared memory is built by one CTA (kdsmall_kernel, 1024 threads): about
-        // 0.1 ms per wave of 148 clouds against 49 grid-wide launches (0.77 ms at BASELINE.json cfg 3)
-        L->small = !getenv("FPS_B200_GRIDBUILD") && plan_kdsmall(n, dim, h, B, n_sms, &L->sp);
-        if (L->small) L->gridbuild = false;
-        L->region_off = (((L->small && L->sp.ws_bytes > L->pl.ws_bytes) ? L->sp.ws_bytes : L->pl.ws_bytes) + 255) & ~(size_t)255;
-        L->region_stride = kd_region_bytes(n, dim, h);
-        L->aux_off = L->region_off + B * L->region_stride;
-        L->total = L->aux_off + (L->gridbuild ? B * kd_gridbuild_aux_bytes(n, dim, h) : 0);
-        if (L->grid) {
-            L->pub_off = (L->total + 255) & ~(size_t)255;
-            L->total = L->pub_off + kd_grid_pub_bytes(L->gp);
-            if (ids) {   // the reversed SoA copy of the input
-                L->qv_off = (L->total + 255) & ~(size_t)255;
-                L->total = L->qv_off + B * dim * ((n + 31) & ~(size_t)31) * sizeof(float);
-            }
+
+    // ---- the builder that fills the regions ---------------------------------------------------------------------------
+    bool gridbuild;
+    if (L->sampler == Sampler::BuildOnly) {
+        gridbuild = false;
+    } else if (L->sampler == Sampler::WarpOnChip || L->sampler == Sampler::WarpStream) {
+        have_small = plan_kdsmall(n, dim, h, B, n_sms, &L->sp);
+        // clouds that stay in global memory: the grid-wide per-level launches build a batch faster than one CTA per cloud
+        // working out of L2 (scripts/cmp_build5.py: 512 x 100 k points 10.9 -> 6.4 ms)
+        gridbuild = !have_small && (tu.gridbuild >= 0 ? tu.gridbuild != 0 : L->sampler == Sampler::WarpStream);
+    } else {
+        // few clouds: one CTA per cloud would idle most SMs -> grid-wide; a cloud whose coordinates fit one SM's shared memory is
+        // built by one CTA (0.1 ms per wave of 148 clouds against 49 grid-wide launches, 0.77 ms at BASELINE.json cfg 3)
+        have_small = tu.gridbuild < 0 && plan_kdsmall(n, dim, h, B, n_sms, &L->sp);
+        gridbuild = !have_small && (tu.gridbuild >= 0 ? tu.gridbuild != 0
+                                                      : (B * 2 <= (size_t)n_sms || n >= route::kGridBuildMinPoints || !cloud_in_one_sm));
+    }
+    L->builder = have_small ? Builder::Small : gridbuild ? Builder::GridWide : Builder::PerCloud;
+
+    // ---- workspace: [builder scratch][regions][256 B counter][grid-wide build aux][grid sampler exchange][reversed input] ----
+    const size_t head = (have_small && L->sp.ws_bytes > L->pl.ws_bytes) ? L->sp.ws_bytes : L->pl.ws_bytes;
+    L->region_off = align256(head);
+    L->region_stride = kd_region_bytes(n, dim, h);
+    L->counter_off = L->region_off + B * L->region_stride;
+    L->total = L->counter_off + 256;
+    if (gridbuild) {
+        L->aux_off = align256(L->total);
+        L->total = L->aux_off + B * kd_gridbuild_aux_bytes(n, dim, h);
+    }
+    if (L->sampler == Sampler::Grid) {
+        L->pub_off = align256(L->total);
+        L->total = L->pub_off + kd_grid_pub_bytes(L->gp);
+        if (ids) {   // the reversed SoA copy of the input
+            L->qv_off = align256(L->total);
+            L->total = L->qv_off + B * dim * ((n + 31) & ~(size_t)31) * sizeof(float);
         }
     }
     return cudaSuccess;
@@ -347,8 +438,7 @@ static cudaError_t kd_layout(size_t B, size_t n, size_t dim, size_t h, int n_sms
 // vanilla FPS on big clouds: the same exact recurrence, pruned.  A kd permutation (height chosen here: leaves of ~128-256
 // points) groups the points into slices; ties are decided by the original index, so the result is fps_sampling's own.
 static bool vanilla_kd_layout(size_t B, size_t n, size_t dim, size_t n_starts, int n_sms, size_t *h, size_t *total) {
-    int want = -1;
-    if (const char *e = getenv("FPS_B200_VANILLA_KD")) want = atoi(e);
+    const int want = tuning().vanilla_kd;
     if (want == 0 || dim > FPS_B200_MAX_KDLINE_DIM || n_starts > 256 || n_starts == 0) return false;
     if (want < 0 && n < 16384) return false;   // smaller clouds: brute force in registers (vanilla_cluster_kernel) wins
     if (n < 2048) return false;
@@ -375,6 +465,7 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         set_err("workspace too small or misaligned: need %zu bytes, 256-byte aligned (got %zu)", L.total, ws_bytes);
         return FPS_ERR_WORKSPACE;
     }
+    unsigned char *w = static_cast<unsigned char *>(ws);
     KdlineArgs a;
     memset(&a, 0, sizeof(a));
     a.pts = d_pts;
@@ -388,52 +479,61 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
     a.dim = (u32)dim;
     a.k = (u32)k;
     a.h = (u32)h;
+    if (L.builder != Builder::Fused) {
+        a.region = w + L.region_off;
+        a.region_stride = L.region_stride;
+    }
     // the build that fills the per-cloud regions, by plan
     auto build_regions = [&]() -> int {
-        if (L.small)
+        if (L.builder == Builder::Small)
             CK(launch_kdsmall(L.sp, d_pts, a.region, a.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
-        else if (L.gridbuild)
-            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, static_cast<unsigned char *>(ws) + L.aux_off, (u32)B,
-                                   (u32)n, (u32)dim, (u32)h, st));
+        else if (L.builder == Builder::GridWide)
+            CK(launch_kd_gridbuild(d_pts, a.region, a.region_stride, w + L.aux_off, (u32)B, (u32)n, (u32)dim, (u32)h, st));
         else
-            CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+            CK(launch_kdline(pl, a, w, st));
         return FPS_OK;
     };
     char bdesc[128];
-    if (L.small)
+    if (L.builder == Builder::Small)
         snprintf(bdesc, sizeof bdesc, "kdsmall_kernel<DIM=%d,T=%d>(build in shared memory, %u CTA%s per SM, smem=%zu)", L.sp.dimp,
                  L.sp.big ? 1024 : 256, L.sp.occ, L.sp.occ > 1 ? "s" : "", L.sp.smem);
     else
-        snprintf(bdesc, sizeof bdesc, "%s", L.gridbuild ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)");
-    if (d_out == nullptr && L.small) {
-        unsigned char *region = static_cast<unsigned char *>(ws) + L.region_off;
-        set_plan("kdsmall_kernel<DIM=%d>(build only, %u CTAs per SM, smem=%zu) + kdsmall_export_kernel", L.sp.dimp, L.sp.occ, L.sp.smem);
-        tl_phase.mark(0, st);
-        CK(launch_kdsmall(L.sp, d_pts, region, L.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
-        CK(launch_kdsmall_export(region, L.region_stride, (u32)B, (u32)n, (u32)dim, (u32)h, perm_out, leaf_lo_out, leaf_box_out, st));
-        tl_phase.mark(1, st);
-        tl_phase.mark(2, st);
-        return FPS_OK;
-    }
-    if (L.warp) {
-        a.region = static_cast<unsigned char *>(ws) + L.region_off;
-        a.region_stride = L.region_stride;
+        snprintf(bdesc, sizeof bdesc, "%s", L.builder == Builder::GridWide ? "gb_* grid-wide build (7 launches per level)" : "kdline_kernel(build, 1 CTA per cloud)");
+    switch (L.sampler) {
+    case Sampler::BuildOnly:
+        if (L.builder == Builder::Small) {
+            set_plan("kdsmall_kernel<DIM=%d>(build only, %u CTAs per SM, smem=%zu) + kdsmall_export_kernel", L.sp.dimp, L.sp.occ, L.sp.smem);
+            tl_phase.mark(0, st);
+            CK(launch_kdsmall(L.sp, d_pts, a.region, a.region_stride, static_cast<u32 *>(ws), (u32)B, (u32)n, (u32)dim, (u32)h, st));
+            CK(launch_kdsmall_export(a.region, a.region_stride, (u32)B, (u32)n, (u32)dim, (u32)h, perm_out, leaf_lo_out, leaf_box_out, st));
+            tl_phase.mark(1, st);
+            tl_phase.mark(2, st);
+            return FPS_OK;
+        }
+        break;   // the fused kernel's build phase, below
+    case Sampler::WarpOnChip:
         set_plan("%s + kdline_warp%s_kernel<DIM=%d,BPL=%u> %s R=%u clouds=%zu grid=%u "
                  "warps/CTA=%u (tmem %u + smem %u) smem=%zu store/cloud=%u",
-                 bdesc, L.wp.global ? "g" : (L.wp.hybrid ? "(hybrid smem+tmem)" : ""), L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
+                 bdesc, L.wp.hybrid ? "(hybrid smem+tmem)" : "", L.wp.dimp, L.wp.bpl, L.wp.lazy ? "lazy" : "eager", L.wp.rs, B, L.wp.grid, L.wp.n_tmem_warps + L.wp.n_smem_warps, L.wp.n_tmem_warps,
                  L.wp.n_smem_warps, L.wp.smem, L.wp.slot_bytes);
         tl_phase.mark(0, st);
         if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
-        CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out,
-                              reinterpret_cast<u32 *>(static_cast<unsigned char *>(ws) + L.counter_off), (u32)B, (u32)n,
+        CK(launch_kdline_warp(L.wp, a.region, a.region_stride, d_starts, d_out, reinterpret_cast<u32 *>(w + L.counter_off), (u32)B, (u32)n,
                               (u32)dim, (u32)k, (u32)h, st));
         tl_phase.mark(2, st);
         return FPS_OK;
-    }
-    if (L.grid) {
-        a.region = static_cast<unsigned char *>(ws) + L.region_off;
-        a.region_stride = L.region_stride;
+    case Sampler::WarpStream:
+        set_plan("%s + kdline_stream_kernel<DIM=%d,WPC=%u,BPL=%u> (points in HBM, %u warp%s per cloud) R=%u clouds=%zu grid=%u smem=%zu",
+                 bdesc, L.stp.dimp, L.stp.wpc, L.stp.bpl, L.stp.wpc, L.stp.wpc > 1 ? "s" : "", L.stp.rs, B, L.stp.grid, L.stp.smem);
+        tl_phase.mark(0, st);
+        if (int rcb = build_regions()) return rcb;
+        tl_phase.mark(1, st);
+        CK(launch_kdline_stream(L.stp, a.region, a.region_stride, d_starts, d_out, reinterpret_cast<u32 *>(w + L.counter_off), (u32)B, (u32)n,
+                                (u32)dim, (u32)k, (u32)h, tuning().count == 1, st));
+        tl_phase.mark(2, st);
+        return FPS_OK;
+    case Sampler::Grid:
         tl_phase.mark(0, st);
         set_plan("%s%s + kdline_grid_kernel<DIM=%d,%s> clouds=%zu grid=%u (%u CTAs per cloud, %u clouds in flight) threads=1024 "
                  "points/thread=%u candidates/round<=%u smem=%zu region/cloud=%zu",
@@ -443,31 +543,13 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
         a.starts = van_pts ? nullptr : d_starts;   // (the build kernels never read it)
-        CK(launch_kdline_grid(L.gp, a.region, a.region_stride, d_starts, d_out, static_cast<unsigned char *>(ws) + L.pub_off,
+        CK(launch_kdline_grid(L.gp, a.region, a.region_stride, d_starts, d_out, w + L.pub_off,
                               (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h, st, van_pts,
-                              van_pts ? reinterpret_cast<float *>(static_cast<unsigned char *>(ws) + L.qv_off) : nullptr,
+                              van_pts ? reinterpret_cast<float *>(w + L.qv_off) : nullptr,
                               (u32)van_nstarts));
         tl_phase.mark(2, st);
         return FPS_OK;
-    }
-    if (L.dist) {
-        a.region = static_cast<unsigned char *>(ws) + L.region_off;
-        a.region_stride = L.region_stride;
-        tl_phase.mark(0, st);
-        set_plan("%s + kdline_dist_kernel<DIM=%d> clouds=%zu clusters=%u cluster=%u threads=%u buckets/CTA=%u "
-                 "candidates/CTA=%u smem=%zu region/cloud=%zu",
-                 bdesc,
-                 L.dp.dimp, B, L.dp.clusters, L.dp.C, L.dp.threads, L.dp.NB, L.dp.M, L.dp.smem, L.region_stride);
-        if (int rcb = build_regions()) return rcb;
-        tl_phase.mark(1, st);
-        CK(launch_kdline_dist(L.dp, a.region, a.region_stride, d_starts, d_out, (u32)B, (u32)n, (u32)dim, (u32)k, (u32)h,
-                              st));
-        tl_phase.mark(2, st);
-        return FPS_OK;
-    }
-    if (L.async) {
-        a.region = static_cast<unsigned char *>(ws) + L.region_off;
-        a.region_stride = L.region_stride;
+    case Sampler::AsyncCluster:
         tl_phase.mark(0, st);
         set_plan("%s + kdline_async_kernel<DIM=%d> clouds=%zu clusters=%u "
                  "cluster=%u threads=%u smem=%zu R=%u region/cloud=%zu",
@@ -479,13 +561,17 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
                                (u32)h, st));
         tl_phase.mark(2, st);
         return FPS_OK;
+    case Sampler::FusedCta:
+        break;
     }
     set_plan("kdline_kernel<DIM=%d> clouds=%zu grid=%u threads=%u smem=%zu placement=%s ws/cta=%zu", pl.dimp, B, pl.grid,
              pl.threads, pl.smem, pl.in_smem == 3 ? "smem" : (pl.in_smem == 2 ? "meta-smem,data-L2" : "L2"),
              pl.ws_stride);
     tl_phase.mark(0, st);
     tl_phase.mark(1, st);
-    CK(launch_kdline(pl, a, static_cast<unsigned char *>(ws), st));
+    a.region = nullptr;
+    a.region_stride = 0;
+    CK(launch_kdline(pl, a, w, st));
     tl_phase.mark(2, st);
     return FPS_OK;
 }
@@ -537,21 +623,16 @@ struct ShardJob {
     const size_t *start;  // per cloud [B][n_starts] or nullptr
     size_t n_starts;
     size_t *out;
+    bool keep_dev = false;   // leave the indices in cx->gout ([B][k] uint64 on the device) instead of copying them to `out`
 };
 
-static int run_shard(int dev, const ShardJob &j) {
-    DevCtx *cx = get_ctx(dev);
-    if (!cx) {
-        set_err("device %d is not a usable sm_100 device", dev);
-        return FPS_ERR_NO_DEVICE;
-    }
-    std::lock_guard<std::mutex> lk(cx->mu);
-    CK(cudaSetDevice(dev));
-    if (!cx->ready) {
-        for (auto &ln : cx->lane) CK(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
-        for (auto &e : cx->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        cx->ready = true;
-    }
+// the stream that produced a device-resident input (set by fps_b200_set_producer_stream for the calling thread's next call);
+// default: the legacy default stream, which orders behind every blocking stream of the caller
+static thread_local cudaStream_t tl_producer = cudaStreamLegacy;
+
+static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
+    const int dev = cx->dev;
+    const Tuning &tu = tuning();
     const size_t in_per = j.n * j.dim * sizeof(float), out_per = j.k * sizeof(u64);
     // input already in this device's memory (a pointer from cudaMalloc, torch, cupy ...): no upload, the kernels read it
     bool dev_in = false;
@@ -563,7 +644,10 @@ static int run_shard(int dev, const ShardJob &j) {
                 return FPS_ERR_ARG;
             }
             dev_in = true;
-            CK(cudaDeviceSynchronize());   // whatever produced the buffer (on any stream of the caller) has finished
+            // whatever produced the buffer is ordered before our lanes by an event on the producer's stream: no device-wide
+            // synchronisation, the caller's other streams keep running
+            CK(cudaEventRecord(cx->ev_in, producer));
+            for (auto &ln : cx->lane) CK(cudaStreamWaitEvent(ln.st, cx->ev_in, 0));
         } else {
             cudaGetLastError();
         }
@@ -584,10 +668,10 @@ static int run_shard(int dev, const ShardJob &j) {
     // One batch of small clouds (the on-chip sampler wants all of them in one launch): the upload is cut into pieces and
     // every piece is BUILT (kdsmall_kernel, into its clouds' regions) while the next one is still crossing PCIe; the
     // sampler then runs once over the whole batch.  Copy engine on lane 0's stream, kernels on lane 1's.
-    if (!dev_in && j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && !getenv("FPS_B200_NO_PIPE")) {
+    if (!dev_in && j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && tu.pipe != 0) {
         KdLayout L;
         CK(kd_layout(j.B, j.n, j.dim, j.h, cx->n_sms, false, &L));
-        if (L.warp && L.small) {
+        if ((L.sampler == Sampler::WarpOnChip || L.sampler == Sampler::WarpStream) && L.builder == Builder::Small) {
             Lane &cp = cx->lane[0], &ex = cx->lane[1];
             if ((rc = cp.in.ensure(j.B * in_per)) || (rc = cp.out.ensure(j.B * out_per)) || (rc = cp.ws.ensure(L.total))) return rc;
             u64 *d_starts = nullptr;
@@ -618,9 +702,9 @@ static int run_shard(int dev, const ShardJob &j) {
             }
             // page-locked output (what the python module hands out): the sampler writes its 32-pick blocks straight into
             // host memory over PCIe while it runs, no device-to-host copy afterwards
-            u64 *d_out = static_cast<u64 *>(cp.out.p);
+            u64 *d_out = static_cast<u64 *>(j.keep_dev ? cx->gout.p : cp.out.p);
             bool zero_copy = false;
-            if (!getenv("FPS_B200_NO_ZEROCOPY")) {
+            if (tu.zerocopy != 0 && !j.keep_dev) {
                 cudaPointerAttributes at;
                 if (cudaPointerGetAttributes(&at, j.out) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) {
                     d_out = static_cast<u64 *>(at.devicePointer);
@@ -629,23 +713,22 @@ static int run_shard(int dev, const ShardJob &j) {
                     cudaGetLastError();
                 }
             }
-            CK(launch_kdline_warp(L.wp, region, L.region_stride, d_starts, d_out,
-                                  reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
-                                  ex.st));
-            if (!zero_copy) CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
-            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + kdline_warp_kernel<DIM=%d,BPL=%u> clouds=%zu grid=%u%s",
-                     c, L.sp.dimp, L.wp.dimp, L.wp.bpl, j.B, L.wp.grid, zero_copy ? " + indices written straight to page-locked host memory" : "");
-            for (auto &ln : cx->lane) {
-                cudaError_t e = cudaStreamSynchronize(ln.st);
-                if (e != cudaSuccess && rc == FPS_OK) {
-                    set_err("kernel execution failed: %s", cudaGetErrorString(e));
-                    rc = FPS_ERR_CUDA + (int)e;
-                }
-            }
-            return rc;
+            if (L.sampler == Sampler::WarpOnChip)
+                CK(launch_kdline_warp(L.wp, region, L.region_stride, d_starts, d_out,
+                                      reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
+                                      ex.st));
+            else
+                CK(launch_kdline_stream(L.stp, region, L.region_stride, d_starts, d_out,
+                                        reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
+                                        false, ex.st));
+            if (!zero_copy && !j.keep_dev) CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
+            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + %s clouds=%zu%s",
+                     c, L.sp.dimp, L.sampler == Sampler::WarpOnChip ? "kdline_warp_kernel" : "kdline_stream_kernel", j.B,
+                     zero_copy ? " + indices written straight to page-locked host memory" : "");
+            return FPS_OK;
         }
     }
-    for (size_t c = 0, b0 = 0; b0 < j.B && rc == FPS_OK; ++c, b0 += chunk) {
+    for (size_t c = 0, b0 = 0; b0 < j.B; ++c, b0 += chunk) {
         const size_t nb = (j.B - b0 < chunk) ? j.B - b0 : chunk;
         Lane &ln = cx->lane[c & 1];
         size_t ws_need;
@@ -664,18 +747,19 @@ static int run_shard(int dev, const ShardJob &j) {
             CK(kd_layout(nb, j.n, j.dim, j.h, cx->n_sms, false, &L));
             ws_need = L.total;
         }
-        if ((!dev_in && (rc = ln.in.ensure(nb * in_per))) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) break;
+        if ((!dev_in && (rc = ln.in.ensure(nb * in_per))) || (rc = ln.out.ensure(nb * out_per)) || (rc = ln.ws.ensure(ws_need))) return rc;
         const float *d_in = dev_in ? j.pts + b0 * j.n * j.dim : static_cast<const float *>(ln.in.p);
+        u64 *d_res = j.keep_dev ? static_cast<u64 *>(cx->gout.p) + b0 * j.k : static_cast<u64 *>(ln.out.p);
         u64 *d_starts = nullptr;
         if (j.start) {
-            if ((rc = ln.starts.ensure(nb * j.n_starts * sizeof(u64)))) break;
+            if ((rc = ln.starts.ensure(nb * j.n_starts * sizeof(u64)))) return rc;
             d_starts = static_cast<u64 *>(ln.starts.p);
             CK(cudaMemcpyAsync(d_starts, j.start + b0 * j.n_starts, nb * j.n_starts * sizeof(u64),
                                cudaMemcpyHostToDevice, ln.st));
         }
         if (!dev_in) CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
         if (j.algo == FPS_ALGO_NPDU) {
-            cudaError_t e = launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, static_cast<u64 *>(ln.out.p), ln.ws.p,
+            cudaError_t e = launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, d_res, ln.ws.p,
                                         cx->n_sms, ln.st);
             if (e == cudaErrorNotSupported) {
                 cudaGetLastError();
@@ -688,18 +772,40 @@ static int run_shard(int dev, const ShardJob &j) {
                 set_plan("npdu_kernel clouds=%zu (one CTA per cloud, 256-point segment maxima in shared memory) window=%zu", nb, j.h);
             }
         } else if (j.algo == FPS_ALGO_VANILLA)
-            rc = enqueue_vanilla(d_in, nb, j.n, j.dim, j.k, d_starts, j.n_starts,
-                                 static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
+            rc = enqueue_vanilla(d_in, nb, j.n, j.dim, j.k, d_starts, j.n_starts, d_res, ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else if (j.algo == FPS_ALGO_KDTREE)
-            rc = enqueue_kdtree(d_in, nb, j.n, j.dim, j.k, d_starts,
-                                static_cast<u64 *>(ln.out.p), ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
+            rc = enqueue_kdtree(d_in, nb, j.n, j.dim, j.k, d_starts, d_res, ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
         else
-            rc = enqueue_kdline(d_in, nb, j.n, j.dim, j.k, d_starts, j.h,
-                                static_cast<u64 *>(ln.out.p), nullptr, nullptr, nullptr, ln.ws.p, ln.ws.cap,
+            rc = enqueue_kdline(d_in, nb, j.n, j.dim, j.k, d_starts, j.h, d_res, nullptr, nullptr, nullptr, ln.ws.p, ln.ws.cap,
                                 cx->n_sms, ln.st);
-        if (rc) break;
-        CK(cudaMemcpyAsync(j.out + b0 * j.k, ln.out.p, nb * out_per, cudaMemcpyDeviceToHost, ln.st));
+        if (rc) return rc;
+        if (!j.keep_dev) CK(cudaMemcpyAsync(j.out + b0 * j.k, ln.out.p, nb * out_per, cudaMemcpyDeviceToHost, ln.st));
     }
+    return FPS_OK;
+}
+
+// One shard on one device.  The caller's current device is restored on every exit path, and BOTH lanes are drained before
+// returning -- also after an error: copies into the caller's `out` (or zero-copy kernel writes into it) may still be queued,
+// and the lane buffers are reused by the next call.
+static int run_shard(int dev, const ShardJob &j) {
+    DevCtx *cx = get_ctx(dev);
+    if (!cx) {
+        set_err("device %d is not a usable sm_100 device", dev);
+        return FPS_ERR_NO_DEVICE;
+    }
+    const cudaStream_t producer = tl_producer;
+    tl_producer = cudaStreamLegacy;   // one call only
+    std::lock_guard<std::mutex> lk(cx->mu);
+    DeviceGuard guard;
+    CK(cudaSetDevice(dev));
+    if (!cx->ready) {
+        for (auto &ln : cx->lane) CK(cudaStreamCreateWithFlags(&ln.st, cudaStreamNonBlocking));
+        for (auto &e : cx->ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&cx->ev_in, cudaEventDisableTiming));
+        cx->ready = true;
+    }
+    int rc = j.keep_dev ? cx->gout.ensure(j.B * j.k * sizeof(u64)) : FPS_OK;
+    if (rc == FPS_OK) rc = shard_enqueue(cx, j, producer);
     for (auto &ln : cx->lane) {
         cudaError_t e = cudaStreamSynchronize(ln.st);
         if (e != cudaSuccess && rc == FPS_OK) {
@@ -713,10 +819,17 @@ static int run_shard(int dev, const ShardJob &j) {
 static int run_batch(ShardJob j, const int *devices, int n_devices) {
     scan_devices();
     std::vector<int> devs;
-    if (devices && n_devices > 0)
+    if (devices && n_devices > 0) {
         devs.assign(devices, devices + n_devices);
-    else
+    } else if (j.B == 1) {
+        // a single cloud runs where the caller is (one process per GPU: torch.cuda.set_device(local) and no device list)
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) cudaGetLastError();
+        if (cur >= 0 && get_ctx(cur)) devs.push_back(cur);
+        else devs = g_devs;
+    } else {
         devs = g_devs;
+    }
     if (devs.empty()) {
         set_err("no usable CUDA device (need compute capability 10.x); there is no CPU fallback");
         return FPS_ERR_NO_DEVICE;
@@ -770,6 +883,61 @@ static int run_batch(ShardJob j, const int *devices, int n_devices) {
     return FPS_OK;
 }
 
+// ---- multi-GPU with the NCCL gather ------------------------------------------------------------------------
+// Every endpoint of this process (one under torchrun, one per device after fps_b200_comm_init_local) samples its contiguous
+// shard on its own GPU, the indices STAY on the device, and comm.cu gathers them to rank 0 as uint32 over NVLink.
+static void shard_range(size_t n_clouds, int world, int rank, size_t *b0, size_t *nb) {
+    const size_t base = n_clouds / (size_t)world, rem = n_clouds % (size_t)world;
+    *nb = base + ((size_t)rank < rem ? 1 : 0);
+    *b0 = (size_t)rank * base + ((size_t)rank < rem ? (size_t)rank : rem);
+}
+
+static int run_sharded(ShardJob j, size_t n_clouds, u64 *out_rank0) {
+    const int E = comm_local_endpoints(), world = comm_world();
+    if (E < 1) {
+        set_err("no communicator: call fps_b200_comm_init (one process per GPU) or fps_b200_comm_init_local first");
+        return FPS_ERR_NCCL;
+    }
+    scan_devices();
+    // one endpoint: `j.pts` is this rank's shard.  Several: this process holds the whole batch and cuts it itself.
+    std::vector<int> rcs((size_t)E, FPS_OK);
+    std::vector<std::string> errs((size_t)E);
+    std::vector<const u64 *> locals((size_t)E, nullptr);
+    std::vector<std::thread> th;
+    for (int i = 0; i < E; ++i) {
+        size_t b0, nb;
+        shard_range(n_clouds, world, comm_endpoint_rank(i), &b0, &nb);
+        ShardJob s = j;
+        s.B = nb;
+        s.keep_dev = true;
+        s.out = nullptr;
+        if (E > 1) {
+            s.pts = j.pts + b0 * j.n * j.dim;
+            s.start = j.start ? j.start + b0 * j.n_starts : nullptr;
+        }
+        const int dev = comm_endpoint_device(i);
+        DevCtx *cx = get_ctx(dev);
+        if (!cx) {
+            set_err("device %d is not a usable sm_100 device", dev);
+            return FPS_ERR_NO_DEVICE;
+        }
+        auto work = [&, i, s, dev, cx]() {
+            if (s.B) rcs[(size_t)i] = run_shard(dev, s);
+            if (rcs[(size_t)i]) errs[(size_t)i] = tl_err;
+            locals[(size_t)i] = static_cast<const u64 *>(cx->gout.p);
+        };
+        if (E == 1) work();
+        else th.emplace_back(work);
+    }
+    for (auto &t : th) t.join();
+    for (int i = 0; i < E; ++i)
+        if (rcs[(size_t)i]) {
+            set_err("device %d: %s", comm_endpoint_device(i), errs[(size_t)i].c_str());
+            return rcs[(size_t)i];
+        }
+    return comm_gather(locals.data(), nullptr, j.k, n_clouds, out_rank0);
+}
+
 }  // namespace fps
 
 using namespace fps;
@@ -788,21 +956,30 @@ const char *fps_b200_last_error(void) { return tl_err; }
 const char *fps_b200_last_plan(void) { return tl_plan; }
 uint64_t fps_b200_kernel_launches(void) { return g_launches.load(); }
 
-int fps_b200_debug_counters(uint64_t *out16) {
+int fps_b200_debug_counters(int which, uint64_t *out16) {
     if (!out16) return FPS_ERR_ARG;
     CK(cudaDeviceSynchronize());
-    if (getenv("FPS_B200_DBG_WARP"))
-        CK(warp_debug_counters(reinterpret_cast<u64 *>(out16)));
-    else if (getenv("FPS_B200_DBG_BUILD"))
-        CK(kb_debug_counters(reinterpret_cast<unsigned long long *>(out16)));
-    else if (getenv("FPS_B200_DBG_GRID"))
-        CK(grid_debug_counters(reinterpret_cast<u64 *>(out16)));
-    else if (getenv("FPS_B200_DBG_DIST"))
-        CK(dist_debug_counters(reinterpret_cast<u64 *>(out16)));
-    else
-        CK(async_debug_counters(reinterpret_cast<u64 *>(out16)));
+    switch (which) {
+        case FPS_DBG_WARP: CK(warp_debug_counters(reinterpret_cast<u64 *>(out16))); break;
+        case FPS_DBG_BUILD: CK(kb_debug_counters(reinterpret_cast<unsigned long long *>(out16))); break;
+        case FPS_DBG_GRID: CK(grid_debug_counters(reinterpret_cast<u64 *>(out16))); break;
+        case FPS_DBG_ASYNC: CK(async_debug_counters(reinterpret_cast<u64 *>(out16))); break;
+        case FPS_DBG_STREAM: CK(stream_debug_counters(reinterpret_cast<u64 *>(out16))); break;
+        default: set_err("unknown counter set %d", which); return FPS_ERR_ARG;
+    }
     return FPS_OK;
 }
+
+int fps_b200_set_tuning(const char *name, long value) {
+    (void)tuning();   // the environment is read first, so an explicit setting wins
+    if (!name || !set_knob(name, value)) {
+        set_err("unknown tuning knob '%s'", name ? name : "(null)");
+        return FPS_ERR_ARG;
+    }
+    return FPS_OK;
+}
+
+void fps_b200_set_producer_stream(void *stream) { tl_producer = static_cast<cudaStream_t>(stream); }
 
 void fps_b200_phase_timing(int enable) { g_phase_timing.store(enable ? 1 : 0); }
 
@@ -949,6 +1126,29 @@ int fps_b200_kdline_batch(const float *points, size_t B, size_t n, size_t dim, s
     if ((rc = check_kdline(n, dim, height))) return rc;
     ShardJob j{FPS_ALGO_KDLINE, points, B, n, dim, k, height, start, 1, out};
     return run_batch(j, devices, n_devices);
+}
+
+int fps_b200_kdline_batch_sharded(const float *points, size_t n_clouds, size_t n, size_t dim, size_t k, const size_t *start,
+                                  size_t height, size_t *out_rank0) {
+    if (dim == 0 || dim > FPS_B200_MAX_KDLINE_DIM) {
+        set_err("only 1 to %d dimensions are supported (dim=%zu)", FPS_B200_MAX_KDLINE_DIM, dim);
+        return FPS_ERR_DIM;
+    }
+    static size_t dummy_out;
+    int rc = check_common(points, n_clouds, n, dim, k, &dummy_out);
+    if (rc) return rc;
+    if ((rc = check_kdline(n, dim, height))) return rc;
+    ShardJob j{FPS_ALGO_KDLINE, points, 0, n, dim, k, height, start, 1, nullptr};
+    return run_sharded(j, n_clouds, reinterpret_cast<u64 *>(out_rank0));
+}
+
+int fps_b200_vanilla_batch_sharded(const float *points, size_t n_clouds, size_t n, size_t dim, size_t k, const size_t *start,
+                                   size_t *out_rank0) {
+    static size_t dummy_out;
+    int rc = check_common(points, n_clouds, n, dim, k, &dummy_out);
+    if (rc) return rc;
+    ShardJob j{FPS_ALGO_VANILLA, points, 0, n, dim, k, 0, start, 1, nullptr};
+    return run_sharded(j, n_clouds, reinterpret_cast<u64 *>(out_rank0));
 }
 
 int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_samples, size_t window, size_t start_idx, size_t *out) {

@@ -103,27 +103,27 @@ cudaError_t launch_kdline_async(const AsyncPlan &pl, unsigned char *region, size
 
 cudaError_t async_debug_counters(u64 *out16);
 cudaError_t warp_debug_counters(u64 *out16);
-cudaError_t dist_debug_counters(u64 *out16);
 
 // ---- kd-line, one warp per cloud over prebuilt regions, records in shared memory or tensor memory (kdline_warp.cu) --
 struct WarpPlan {
     int dimp;
-    u32 rs /* pending samples per bucket */, bpl, n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, grid, lazy, nch, global, hybrid;
+    u32 rs /* pending samples per bucket */, bpl, n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, grid, lazy, nch, hybrid;
     size_t smem;
 };
 bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpPlan *pl);
 cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
 
-// ---- kd-line, buckets distributed over the CTAs of a cluster, several picks per DSMEM all-gather (kdline_dist.cu) -----
-struct DistPlan {
+// ---- kd-line, a team of 1 / 2 / 4 warps per cloud over prebuilt regions left in global memory (kdline_stream.cu) --------
+struct StreamPlan {
     int dimp;
-    u32 C, NB, M, threads, clusters;
+    u32 wpc /* warps per cloud */, bpl /* buckets per lane */, rs /* pending samples per bucket */, team_bytes, grid;
     size_t smem;
 };
-bool plan_kdline_dist(size_t n, size_t dim, size_t h, size_t B, int n_sms, DistPlan *pl);
-cudaError_t launch_kdline_dist(const DistPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
-                               u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
+bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl);
+cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
+                                 u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, bool count, cudaStream_t st);
+cudaError_t stream_debug_counters(u64 *out16);   // points scanned, point-updates, flushes, early flushes, bucket tests, picks, clouds
 
 // ---- kd-line, one huge cloud on the whole GPU: points in shared memory, batched picks per grid-wide exchange (kdline_grid.cu) --
 struct GridPlan {
@@ -161,5 +161,27 @@ cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t
 cudaError_t launch_seqsum(const float *x, size_t n, float *out, u32 *fast_tiles, int epl, cudaStream_t st);
 
 void count_launch();
+
+// ---- tuning knobs ------------------------------------------------------------------------------------------------------
+// Read from the environment ONCE (FPS_B200_<NAME>, first use); afterwards only fps_b200_set_tuning changes them.  -1 =
+// the planner's own choice.  The call path reads this struct, never the environment.
+struct Tuning {
+    int grid = -1;            // GRID: 1 forces the whole-GPU / grouped grid sampler, 0 forbids it
+    int group = -1;           // GROUP: 1 forces the grouped (flat) grid sampler, 0 forbids it
+    int gridbuild = -1;       // GRIDBUILD: 1 forces the grid-wide build launches, 0 forbids them
+    int vanilla_kd = -1;      // VANILLA_KD: 1 forces fps_sampling through the kd permutation route, 0 forbids it
+    int pipe = -1;            // PIPE: 0 switches the pipelined upload + per-piece build off
+    int zerocopy = -1;        // ZEROCOPY: 0 never writes indices straight into page-locked host memory
+    int grid_ecap = -1;       // GRID_ECAP: candidates per round of the grid sampler (32..G_ECAP)
+    int warp = -1;            // WARP: 0 forbids the one-warp-per-cloud samplers
+    int warp_tmem = -1;       // WARP_TMEM: 0 keeps the on-chip sampler out of tensor memory
+    int warp_lazy = -1;       // WARP_LAZY: 0 = eager flushes
+    int warp_hybrid = -1;     // WARP_HYBRID: 1 = coordinates in shared memory + distances in TMEM (opt-in)
+    long warp_global_minb = -1;   // WARP_GLOBAL_MINB: smallest batch the streaming sampler takes
+    int kdsmall = -1;         // KDSMALL: 0 forbids the shared-memory build kernel
+    int stream_warps = -1;    // STREAM_WARPS: warps per cloud of the streaming sampler (1, 2, 4)
+    int count = -1;           // COUNT: 1 = the streaming sampler counts the work it executes (fps_b200_debug_counters)
+};
+const Tuning &tuning();
 
 }  // namespace fps

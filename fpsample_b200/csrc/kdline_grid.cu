@@ -825,21 +825,16 @@ size_t kd_grid_pub_bytes(const GridPlan &pl) {
 
 bool plan_kdline_grid(size_t n, size_t dim, size_t h, size_t B, int n_sms, GridPlan *pl, bool ids) {
     if (dim == 0 || dim > 8 || h == 0 || n == 0 || B == 0 || n >= G_PNONE) return false;
-    int want = -1;
-    if (const char *e = getenv("FPS_B200_GRID")) want = atoi(e);
+    const int want = tuning().grid;
     if (want == 0) return false;
     const int dimp = pad_dim_g((int)dim);
     const size_t sms = n_sms < (int)G_MAXG ? n_sms : G_MAXG;
     const size_t S = (size_t)1 << (h < 20 ? h : 20);
     pl->dimp = dimp;
     pl->ecap = G_ECAP;
-    if (const char *e = getenv("FPS_B200_GRID_ECAP")) {
-        const int v = atoi(e);
-        if (v >= 32 && v <= (int)G_ECAP) pl->ecap = (u32)v;
-    }
+    if (const int v = tuning().grid_ecap; v >= 32 && v <= (int)G_ECAP) pl->ecap = (u32)v;
     // ---- a batch of medium clouds: groups of gc <= 8 CTAs per cloud, every warp publishes its own keys (flat mode) ------
-    int grp = -1;
-    if (const char *e = getenv("FPS_B200_GROUP")) grp = atoi(e);
+    const int grp = tuning().group;
     const bool medium = n >= 8192 && n < 262144 && S <= 4096;
     // measured (scripts/cmp_group.py): 1.4x - 3x faster than the cluster coordinator/worker kernel and than the one-warp-per-
     // cloud kernel on every shape from 8192 points up (FPS_B200_GROUP=0 switches it off)

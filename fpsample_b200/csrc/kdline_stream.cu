@@ -1,0 +1,542 @@
+// kdline_stream.cu -- QuickFPS kd-line SAMPLING for big clouds in big batches (BASELINE.json cfg 5: thousands of
+// 100 000-point clouds): the points stay in the per-cloud region in global memory (HBM / L2) and a TEAM of 1, 2 or 4
+// warps samples one cloud.  The governing roofline is HBM bandwidth: a bucket pass reads D coordinates + the running
+// distance of every point of the bucket and writes back the distances that changed -- 4(D+2) bytes per point at most.
+//
+// Semantics (reference src/_ext/KDLineTree.h:56-85, src/_ext/KDNode.h:84-166, src/wrapper.hpp:54-59):
+// exact FPS over the array the kd build permuted, started at POSITION start, running distance initialised to FLT_MAX
+// (src/_ext/Point.h:61-65), ties to the lowest position (strict '>' everywhere).  Buckets (kd leaves) follow the
+// reference's own lazy scheme (KDNode::update_distance, KDNode.h:120-166): a lane owns a bucket -- box, current max, the
+// max point's coordinates -- and per new sample either drops it (box bound >= max, KDNode.h:105-118), defers it to the
+// bucket's pending list (max point not affected, KDNode.h:124-134) or flushes: one pass over the bucket applies every
+// pending sample and recomputes the max (KDNode.h:147-161).  A full pending list flushes early, which is always
+// allowed (the sample is a genuine earlier pick).  Float rounding is monotone, so skipped work never changes a
+// distance and the result equals the eager recurrence bit for bit.
+//
+// What is different from one warp per cloud (kdline_warp.cu, on-chip clouds):
+//   * a bucket pass is split over the team's warps (each takes a contiguous run of 32-position chunks), so a pass is ONE
+//     HBM round trip instead of three or four dependent ones -- what a small shard of a multi-GPU batch needs
+//     (3.5 clouds per SM at 512 clouds: latency-bound);
+//   * loads and stores are predicated per position: nothing outside [lo, hi) of the bucket is read, only distances that
+//     changed are written -- DRAM traffic is the algorithmic traffic (ncu: 1.35x before);
+//   * a lane owns four consecutive positions of a 128-position chunk: 128-bit loads and stores, a quarter of the memory
+//     instructions and address arithmetic of a 32-bit-per-lane layout;
+//   * executed-work counters (points scanned, point-updates, flushes, tests) for the roofline (SURVEY.md 8(d) W_exec).
+// Per pick the team meets at three named barriers (bar.sync id, 32*WPC): after the tests (flush masks + pending
+// entries), after the bucket passes (per-warp partial maxima) and after the arg-max partials.
+#include <cfloat>
+
+#include "common.cuh"
+#include "engine.h"
+
+namespace fps {
+
+constexpr u32 S_NONE = 0xffffffffu;
+constexpr int S_U = 8;              // chunks (of 32 positions) per block of a bucket pass
+constexpr u32 S_MAXF = 8;           // flushed buckets per exchange batch
+constexpr u32 S_THREADS = 512;      // 16 warps per CTA, one CTA per SM (128 registers per thread)
+constexpr u32 S_REC = 48;           // bytes of a partial record: max bits, position, up to 8 coordinates
+constexpr u32 S_MAXR = 16;          // pending samples per bucket at most
+
+__device__ u64 g_stream_wexec[16];
+
+struct StreamArgs {
+    unsigned char *region;
+    size_t region_stride;
+    const u64 *starts;
+    u64 *out;
+    u32 *counter;       // dynamic cloud scheduler
+    u32 B, n, npad, dim, k, S, nlo_pad, R, team_bytes, count;
+    u64 negzero;        // two binary32 -0.0 as an operand the compiler cannot see through (packed products, common.cuh)
+};
+
+template <int WPC>
+__device__ __forceinline__ void team_sync(u32 team) {
+    if constexpr (WPC == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1u), "n"(WPC * 32) : "memory");
+}
+
+__device__ __forceinline__ float4 s_lds128(u32 a) {
+    float4 f;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(a));
+    return f;
+}
+__device__ __forceinline__ void s_sts128(u32 a, float x, float y, float z, float w) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+// point -> box squared distance (KDNode.h:105-118) without branches: the excess along a dimension is
+// max(r - hi, lo - r, 0) -- the same subtraction result the reference's if/else picks, or (+-)0
+template <int DIM>
+__device__ __forceinline__ float s_boxdist(const float (&r)[DIM], const float (&lo)[DIM], const float (&hi)[DIM]) {
+    float acc = 0.0f;
+#pragma unroll
+    for (int j = 0; j < DIM; ++j) {
+        const float e = fmaxf(fmaxf(__fsub_rn(r[j], hi[j]), __fsub_rn(lo[j], r[j])), 0.0f);
+        const float e2 = __fmul_rn(e, e);
+        acc = (j == 0) ? e2 : __fadd_rn(acc, e2);
+    }
+    return acc;
+}
+
+__device__ __forceinline__ u32 lds32(u32 a) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds128u(u32 a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts128u(u32 a, u32 x, u32 y, u32 z, u32 w) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ float4 ldg128(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// One cloud on a team of WPC warps.  A lane owns FOUR consecutive positions of every 128-position chunk (128-bit loads and
+// stores: a warp access is 512 contiguous bytes per component); a bucket pass is cut into runs of chunks, one run per warp.
+template <int DIM, int WPC, int BPL>
+__device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 tm /* shared address */, u32 cnt_s) {
+    constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
+    constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per pending-list entry
+    constexpr u32 NW = WPC * BPL;                  // flush-mask words
+    constexpr int G = 2;                           // 128-position chunks per block: 8 positions per lane in registers
+    const u32 lane = lane_id();
+    const u32 npad = a.npad, dim = a.dim, S = a.S, k = a.k, R = a.R;
+    unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
+    const float *q = reinterpret_cast<const float *>(rg);
+    float *dis = reinterpret_cast<float *>(rg) + (size_t)dim * npad;
+
+    // team shared memory (32-bit shared addresses):
+    // pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} | fmask[NW] | part[2][S_MAXF][WPC] | amax[WPC]
+    const u32 pend = tm;
+    const u32 brec = tm + R * SP * PRB;
+    const u32 fmask = brec + SP * 16;
+    const u32 part = fmask + ((NW + 3) & ~3u) * 4;
+    const u32 amax = part + 2 * S_MAXF * WPC * S_REC;
+
+    // ---- distances start at FLT_MAX (Point.h:61-65); bucket boundaries to shared memory ------------------------------
+    for (u32 p = (tw * 32 + lane) * 4; p < npad; p += WPC * 128)
+        __stcg(reinterpret_cast<float4 *>(dis + p), make_float4(FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX));
+    {
+        const u32 *nlo = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 2) * npad;
+        for (u32 s = tw * 32 + lane; s < SP; s += WPC * 32) {
+            const u32 lo = nlo[s < S ? s : S], hi = nlo[s + 1 < S ? s + 1 : S];
+            sts128u(brec + s * 16, lo, hi, 0u, 0u);
+        }
+    }
+
+    // ---- bucket state in registers: warp tw, slot j, lane l own bucket (tw * BPL + j) * 32 + l -------------------------
+    float blo[BPL][DIM], bhi[BPL][DIM], bmc[BPL][DIM], bmax[BPL];
+    u32 bpos[BPL], np[BPL];
+    u32 valid = 0;
+    team_sync<WPC>(team);
+    {
+        const float *fbox = reinterpret_cast<const float *>(rg) + (size_t)(dim + 2) * npad + a.nlo_pad;
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+            const u32 b = (tw * BPL + j) * 32 + lane;
+            bmax[j] = FLT_MAX;   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103)
+            bpos[j] = 0;
+            np[j] = 0;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) blo[j][c] = bhi[j][c] = bmc[j][c] = 0.0f;
+            const uint4 br = lds128u(brec + b * 16);
+            if (b < S && br.y > br.x) {
+                valid |= 1u << j;
+#pragma unroll
+                for (int c = 0; c < DIM; ++c)
+                    if (c < (int)dim) {
+                        blo[j][c] = fbox[(size_t)b * 2 * dim + c];
+                        bhi[j][c] = fbox[(size_t)b * 2 * dim + dim + c];
+                    }
+            }
+        }
+    }
+
+    u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;   // POSITION in the permuted array (wrapper.hpp:54-55)
+    float r[DIM];
+#pragma unroll
+    for (int c = 0; c < DIM; ++c) r[c] = (c < (int)dim) ? __ldg(q + (size_t)c * npad + cur) : 0.0f;
+    u32 mypos = cur;   // lane (t % 32) remembers pick t until the block of 32 picks is written out
+    u32 idv = 0;       // ids of the block being written out
+    u32 bp = 0;        // parity of the partial-record buffer
+
+    for (u32 t = 1; t < k; ++t) {
+        // ---- 1. every bucket against the new sample: drop / defer / flush (KDNode.h:120-146) ------------------------------
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+            const u32 b = (tw * BPL + j) * 32 + lane;
+            const bool ok = (valid >> j) & 1u;
+            const bool touch = s_boxdist<DIM>(r, blo[j], bhi[j]) < bmax[j];     // can lower something in the bucket
+            const bool hitmax = !(sqdist<DIM>(bmc[j], r) > bmax[j]);            // lowers the bucket's max point
+            const bool want = ok && (touch || hitmax);
+            if (want) {   // remember the sample: pend[np][bucket]
+                const u32 e = pend + (np[j] * SP + b) * PRB;
+                s_sts128(e, r[0], DIM > 1 ? r[DIM > 1 ? 1 : 0] : 0.f, DIM > 2 ? r[DIM > 2 ? 2 : 0] : 0.f, DIM > 3 ? r[DIM > 3 ? 3 : 0] : 0.f);
+                if constexpr (DIM > 4)
+                    s_sts128(e + 16u, r[4], DIM > 5 ? r[DIM > 5 ? 5 : 0] : 0.f, DIM > 6 ? r[DIM > 6 ? 6 : 0] : 0.f, DIM > 7 ? r[DIM > 7 ? 7 : 0] : 0.f);
+                ++np[j];
+                sts32(brec + b * 16 + 8, np[j]);
+            }
+            const bool flush = want && (hitmax || np[j] >= R);
+            const u32 m = __ballot_sync(FULL, flush);
+            if (lane == 0) sts32(fmask + (tw * BPL + j) * 4, m);
+            if (a.count) {
+                const u32 ne = __popc(__ballot_sync(FULL, flush && !hitmax));
+                if (lane == 0 && ne) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 24)), (u64)ne);
+            }
+        }
+        team_sync<WPC>(team);
+
+        // ---- 2. bucket passes: every flushed bucket, this warp's run of chunks, all pending samples applied -----------------
+        u32 mw[NW];
+#pragma unroll
+        for (u32 w = 0; w < NW; ++w) mw[w] = lds32(fmask + w * 4);
+        for (;;) {   // batches of at most S_MAXF buckets between two exchanges
+            u32 nf = 0, myb = S_NONE;                 // lane fi remembers the bucket of flush slot fi
+            const u32 pbuf = part + bp * (S_MAXF * WPC * S_REC);
+            while (nf < S_MAXF) {
+                u32 b = S_NONE;
+#pragma unroll
+                for (u32 w = 0; w < NW; ++w) {
+                    if (b == S_NONE && mw[w]) {
+                        b = w * 32 + (__ffs(mw[w]) - 1);
+                        mw[w] &= mw[w] - 1;
+                    }
+                }
+                if (b == S_NONE) break;
+                const u32 fi = nf++;
+                if (lane == fi) myb = b;
+                const uint4 br = lds128u(brec + b * 16);
+                const u32 lo = br.x, hi = br.y, nref = br.z;
+                const u32 c0 = lo >> 7, ncn = ((hi - 1) >> 7) - c0 + 1, per = (ncn + WPC - 1) / WPC;
+                const u32 my0 = c0 + tw * per, my1 = min(my0 + per, c0 + ncn);
+                if (a.count && tw == 0 && lane == 0) {
+                    u64 *cs = reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s));
+                    atomicAdd(cs + 0, (u64)(hi - lo));
+                    atomicAdd(cs + 1, (u64)(hi - lo) * nref);
+                    atomicAdd(cs + 2, 1ull);
+                }
+                float best = -1.0f;
+                u32 bi = S_NONE;
+                float bc[DIM];
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) bc[c] = 0.0f;
+                for (u32 cb = my0; cb < my1; cb += G) {   // one block: G chunks of 128 positions, 4 per lane each
+                    float4 x[DIM][G], old[G];
+                    bool inside[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const u32 p4 = (cb + g) * 128 + lane * 4;
+                        const bool any = cb + g < my1 && p4 < hi && p4 + 3 >= lo;
+                        inside[g] = cb + g < my1 && p4 >= lo && p4 + 3 < hi;
+                        old[g] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);   // never a maximum, never stored
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) x[c][g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (any) {
+                            old[g] = __ldcg(reinterpret_cast<const float4 *>(dis + p4));
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c)
+                                if (c < (int)dim) x[c][g] = ldg128(q + (size_t)c * npad + p4);
+                            if (!inside[g]) {   // a run's first / last group: positions of the neighbour buckets drop out
+                                if (p4 + 0 < lo || p4 + 0 >= hi) old[g].x = -1.0f;
+                                if (p4 + 1 < lo || p4 + 1 >= hi) old[g].y = -1.0f;
+                                if (p4 + 2 < lo || p4 + 2 >= hi) old[g].z = -1.0f;
+                                if (p4 + 3 < lo || p4 + 3 >= hi) old[g].w = -1.0f;
+                            }
+                        }
+                    }
+                    float4 v[G];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) v[g] = old[g];
+                    // the next pending sample is fetched while the current one is applied
+                    const u32 e0 = pend + b * PRB, estep = SP * PRB;
+                    float4 n0 = s_lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (DIM > 4) n1 = s_lds128(e0 + 16u);
+                    for (u32 i = 0; i < nref; ++i) {
+                        const float4 f0 = n0, f1 = n1;
+                        const u32 en = e0 + min(i + 1, nref - 1) * estep;
+                        n0 = s_lds128(en);
+                        if constexpr (DIM > 4) n1 = s_lds128(en + 16u);
+                        const float w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                        u64 RC[DIM];   // the sample in both halves of a packed operand (FADD2 / FFMA2: two positions per instruction)
+#pragma unroll
+                        for (int c = 0; c < DIM; ++c) RC[c] = pk2(w[c], w[c]);
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            u64 PA[DIM], PB[DIM];
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) PA[c] = pk2(x[c][g].x, x[c][g].y), PB[c] = pk2(x[c][g].z, x[c][g].w);
+                            float d0, d1, d2, d3;
+                            up2(sqdist2<DIM>(PA, RC, a.negzero), d0, d1);
+                            up2(sqdist2<DIM>(PB, RC, a.negzero), d2, d3);
+                            v[g].x = fminf(v[g].x, d0);   // std::min(dis, d), Point.h:82-86
+                            v[g].y = fminf(v[g].y, d1);
+                            v[g].z = fminf(v[g].z, d2);
+                            v[g].w = fminf(v[g].w, d3);
+                        }
+                    }
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        const u32 p4 = (cb + g) * 128 + lane * 4;
+                        const bool ch = v[g].x != old[g].x || v[g].y != old[g].y || v[g].z != old[g].z || v[g].w != old[g].w;
+                        if (ch) {
+                            if (inside[g]) {
+                                __stcg(reinterpret_cast<float4 *>(dis + p4), v[g]);
+                            } else {   // never touch a neighbour bucket's positions: another warp may be writing them
+                                if (v[g].x != old[g].x) __stcg(dis + p4 + 0, v[g].x);
+                                if (v[g].y != old[g].y) __stcg(dis + p4 + 1, v[g].y);
+                                if (v[g].z != old[g].z) __stcg(dis + p4 + 2, v[g].z);
+                                if (v[g].w != old[g].w) __stcg(dis + p4 + 3, v[g].w);
+                            }
+                        }
+                        // ascending positions: a lane keeps its first maximum
+#define S_TRACK(E, OFF)                                              \
+    if (v[g].E > best) {                                             \
+        best = v[g].E;                                               \
+        bi = p4 + OFF;                                               \
+        _Pragma("unroll") for (int c = 0; c < DIM; ++c) bc[c] = x[c][g].E; \
+    }
+                        S_TRACK(x, 0)
+                        S_TRACK(y, 1)
+                        S_TRACK(z, 2)
+                        S_TRACK(w, 3)
+#undef S_TRACK
+                    }
+                }
+                // this warp's maximum of the bucket and its lowest position (a warp without chunks reports "nothing")
+                const float pv = fmaxf(best, 0.0f);
+                const u32 m = __reduce_max_sync(FULL, __float_as_uint(pv));
+                const u32 qpos = __reduce_min_sync(FULL, (__float_as_uint(pv) == m) ? bi : S_NONE);
+                const u32 rec = pbuf + (fi * WPC + tw) * S_REC;
+                if (qpos == S_NONE) {
+                    if (lane == 0) sts32(rec, 0u), sts32(rec + 4, S_NONE);
+                } else if (bi == qpos) {   // positions are unique: exactly one lane
+                    sts32(rec, m);
+                    sts32(rec + 4, qpos);
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) sts32(rec + 8 + c * 4, __float_as_uint(bc[c]));
+                }
+            }
+            if (nf == 0) break;
+            team_sync<WPC>(team);
+            // ---- owners take the bucket's new maximum: largest value, lowest position over the warps' partials ----------------
+            for (u32 fi = 0; fi < nf; ++fi) {
+                const u32 b = __shfl_sync(FULL, myb, fi);
+                if ((b >> 5) / BPL == tw && (b & 31u) == lane) {
+                    u32 m = 0, qpos = S_NONE, src = pbuf + (fi * WPC) * S_REC;
+#pragma unroll
+                    for (int w = 0; w < WPC; ++w) {
+                        const u32 rec = pbuf + (fi * WPC + w) * S_REC;
+                        const u32 mm = lds32(rec), qq = lds32(rec + 4);
+                        if (qq != S_NONE && (qpos == S_NONE || mm > m || (mm == m && qq < qpos))) m = mm, qpos = qq, src = rec;
+                    }
+#pragma unroll
+                    for (int j = 0; j < BPL; ++j)
+                        if (((b >> 5) % BPL) == (u32)j) {
+                            bmax[j] = __uint_as_float(m);
+                            bpos[j] = qpos;
+                            np[j] = 0;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) bmc[j][c] = __uint_as_float(lds32(src + 8 + c * 4));
+                        }
+                    sts32(brec + b * 16 + 8, 0u);
+                }
+            }
+            bp ^= 1u;
+            if (nf < S_MAXF) break;   // the masks are empty
+        }
+
+        // ---- 3. arg-max over buckets: largest max, lowest position (KDLineTree.h:56-67) ----------------------------------
+        u32 kmax = 0, cand = S_NONE;
+        int jbest = 0;
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) {
+            if ((valid >> j) & 1u) {
+                const u32 kb = __float_as_uint(bmax[j]);
+                if (cand == S_NONE || kb > kmax || (kb == kmax && bpos[j] < cand)) {
+                    kmax = kb;
+                    cand = bpos[j];
+                    jbest = j;
+                }
+            }
+        }
+        const u32 M = __reduce_max_sync(FULL, kmax);
+        const u32 mine = (cand != S_NONE && kmax == M) ? cand : S_NONE;
+        const u32 wpos = __reduce_min_sync(FULL, mine);
+        if (wpos == S_NONE) {
+            if (lane == 0) sts32(amax + tw * S_REC, 0u), sts32(amax + tw * S_REC + 4, S_NONE);
+        } else if (mine == wpos) {   // positions are unique: exactly one lane
+            const u32 rec = amax + tw * S_REC;
+            sts32(rec, M);
+            sts32(rec + 4, wpos);
+#pragma unroll
+            for (int j = 0; j < BPL; ++j)
+                if (j == jbest) {
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) sts32(rec + 8 + c * 4, __float_as_uint(bmc[j][c]));
+                }
+        }
+        team_sync<WPC>(team);
+        {
+            u32 m = 0, pos = S_NONE, src = amax;
+#pragma unroll
+            for (int w = 0; w < WPC; ++w) {
+                const u32 rec = amax + w * S_REC;
+                const u32 mm = lds32(rec), qq = lds32(rec + 4);
+                if (qq != S_NONE && (pos == S_NONE || mm > m || (mm == m && qq < pos))) m = mm, pos = qq, src = rec;
+            }
+            cur = pos;
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) r[c] = __uint_as_float(lds32(src + 8 + c * 4));
+        }
+        // ---- output: positions are turned into original ids 32 picks at a time (wrapper.hpp:57-59) -----------------
+        if (tw == 0) {
+            const u32 *perm = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 1) * npad;
+            u64 *out = a.out + (size_t)cloud * k;
+            if ((t & 31u) == 0) idv = __ldg(perm + mypos);
+            if ((t & 31u) == 1 && t > 1) out[t - 33 + lane] = (u64)idv;
+            if (lane == (t & 31u)) mypos = cur;
+        }
+    }
+    if (tw == 0) {
+        const u32 *perm = reinterpret_cast<const u32 *>(rg) + (size_t)(dim + 1) * npad;
+        u64 *out = a.out + (size_t)cloud * k;
+        if (k > 32 && ((k - 1) & 31u) == 0) out[k - 33 + lane] = (u64)idv;   // the block whose lookup the last pick issued
+        const u32 k0 = (k - 1) & ~31u;   // tail: picks [k0, k)
+        if (k0 + lane < k) out[k0 + lane] = (u64)__ldg(perm + mypos);
+    }
+    if (a.count && lane == 0 && tw == 0) {
+        u64 *cs = reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s));
+        atomicAdd(cs + 4, (u64)(k - 1) * S);   // bucket tests
+        atomicAdd(cs + 5, (u64)(k - 1));       // picks
+        atomicAdd(cs + 6, 1ull);               // clouds
+    }
+    team_sync<WPC>(team);   // the team's shared memory is reused by its next cloud
+}
+
+template <int DIM, int WPC, int BPL>
+__global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 sched[S_THREADS / 32];
+    __shared__ u64 cnt[8];   // executed work of this CTA (a.count)
+    const u32 warp = warp_id(), lane = lane_id();
+    const u32 team = warp / WPC, tw = warp % WPC;
+    constexpr u32 teams = S_THREADS / 32 / WPC;
+    if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    // first wave: cloud = team * gridDim + cta (few clouds spread over SMs before they stack up on one); afterwards
+    // clouds are handed out dynamically
+    u32 cloud = team * gridDim.x + blockIdx.x;
+    while (cloud < a.B) {
+        stream_cloud<DIM, WPC, BPL>(a, cloud, team, tw, smem_u32(smem_raw) + team * a.team_bytes, smem_u32(cnt));
+        if (tw == 0 && lane == 0) sched[team] = atomicAdd(a.counter, 1u) + teams * gridDim.x;
+        team_sync<WPC>(team);
+        cloud = sched[team];
+    }
+    if (a.count) {
+        __syncthreads();
+        if (threadIdx.x < 8) atomicAdd(&g_stream_wexec[threadIdx.x], cnt[threadIdx.x]);
+    }
+}
+
+// ======================================================================================================
+//  host side
+// ======================================================================================================
+static int stream_dim(int dim) { return dim <= 3 ? 3 : dim == 4 ? 4 : dim <= 6 ? 6 : 8; }
+
+static size_t stream_team_bytes(int dimp, u32 wpc, u32 bpl, u32 R) {
+    const size_t SP = 32u * wpc * bpl, PRB = (size_t)((dimp + 3) / 4) * 16, NW = wpc * bpl;
+    size_t b = R * SP * PRB;
+    b += SP * 16 + ((NW + 3) & ~(size_t)3) * 4;
+    b += 2 * S_MAXF * wpc * S_REC + wpc * S_REC;
+    return (b + 15) & ~(size_t)15;
+}
+
+bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl) {
+    if (dim == 0 || dim > 8 || h == 0 || h > 9 || n == 0 || B == 0) return false;
+    const Tuning &tu = tuning();
+    const u32 S = 1u << h;
+    const int dimp = stream_dim((int)dim);
+    const size_t cap = 227 * 1024 - 256;
+    // warps per cloud: 4 (measured, 100 k-point clouds x 3, 2^7 buckets: a 512-cloud shard samples in 31.8 ms with 4 warps per
+    // cloud, 56 ms with 2, 94 ms with 1; 4096 clouds take 218 - 231 ms whichever way the 16 warps of an SM are grouped -- the
+    // pick is a dependent chain, an SM only overlaps as many of them as it has teams); 1 and 2 stay available as a knob
+    u32 wpc = 4;
+    if (tu.stream_warps == 1 || tu.stream_warps == 2 || tu.stream_warps == 4) wpc = (u32)tu.stream_warps;
+    if (S > 128) wpc = 4;
+    const u32 bpl = wpc == 1 ? 4 : wpc == 2 ? 2 : (S <= 128 ? 1 : S <= 256 ? 2 : 4);
+    const u32 teams = S_THREADS / 32 / wpc;
+    u32 R = S_MAXR;
+    while (R > 2 && teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) --R;
+    if (teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) return false;
+    pl->dimp = dimp;
+    pl->wpc = wpc;
+    pl->bpl = bpl;
+    pl->rs = R;
+    pl->team_bytes = (u32)stream_team_bytes(dimp, wpc, bpl, R);
+    pl->smem = (size_t)teams * pl->team_bytes;
+    pl->grid = (u32)(B < (size_t)n_sms ? B : (size_t)n_sms);   // spread over every SM before stacking teams
+    return true;
+}
+
+template <int DIM, int WPC, int BPL>
+static cudaError_t launch_stream_t(const StreamPlan &pl, const StreamArgs &a, cudaStream_t st) {
+    auto kern = kdline_stream_kernel<DIM, WPC, BPL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<pl.grid, S_THREADS, pl.smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int DIM>
+static cudaError_t launch_stream_d(const StreamPlan &pl, const StreamArgs &a, cudaStream_t st) {
+    if (pl.wpc == 1) return launch_stream_t<DIM, 1, 4>(pl, a, st);
+    if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2>(pl, a, st);
+    if (pl.bpl == 1) return launch_stream_t<DIM, 4, 1>(pl, a, st);
+    if (pl.bpl == 2) return launch_stream_t<DIM, 4, 2>(pl, a, st);
+    return launch_stream_t<DIM, 4, 4>(pl, a, st);
+}
+
+cudaError_t stream_debug_counters(u64 *out16) { return cudaMemcpyFromSymbol(out16, g_stream_wexec, sizeof(u64) * 16); }
+
+cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
+                                 u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, bool count, cudaStream_t st) {
+    StreamArgs a;
+    a.region = region;
+    a.region_stride = region_stride;
+    a.starts = starts;
+    a.out = out;
+    a.counter = counter;
+    a.B = B;
+    a.n = n;
+    a.npad = (n + 31) & ~31u;
+    a.dim = dim;
+    a.k = k;
+    a.S = 1u << h;
+    a.nlo_pad = (a.S + 1 + 31) & ~31u;
+    a.R = pl.rs;
+    a.team_bytes = pl.team_bytes;
+    a.count = count ? 1u : 0u;
+    a.negzero = 0x8000000080000000ull;
+    cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
+    if (e != cudaSuccess) return e;
+    if (count) {
+        void *sym = nullptr;
+        if ((e = cudaGetSymbolAddress(&sym, g_stream_wexec)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(sym, 0, sizeof(u64) * 16, st)) != cudaSuccess) return e;
+    }
+    switch (pl.dimp) {
+        case 3: e = launch_stream_d<3>(pl, a, st); break;
+        case 4: e = launch_stream_d<4>(pl, a, st); break;
+        case 6: e = launch_stream_d<6>(pl, a, st); break;
+        default: e = launch_stream_d<8>(pl, a, st); break;
+    }
+    count_launch();
+    return e;
+}
+
+}  // namespace fps

@@ -197,47 +197,6 @@ struct HybridStore {
     }
 };
 
-// Points stay in the per-cloud region in global memory (L2 / HBM): for big clouds in big batches, where throughput
-// comes from hundreds of clouds in flight (one warp each) and the governing roofline is HBM bandwidth -- 4(D+2)
-// bytes per point-update.  A warp access is 32 consecutive positions = one 128-byte line per component.
-template <bool WIDE>
-struct GlobalStoreT {
-    static constexpr bool kTrackCoords = true;   // a point lookup would be an L2 / HBM round trip on the pick path
-    static constexpr bool kCoordsInPlace = true; // the region already holds the coordinates: only distances are staged
-    static constexpr bool kWide = WIDE;          // 16-chunk blocks (few clouds per SM: bytes in flight per warp matter)
-    const float *q;   // [dim][npad]
-    float *dis;       // [npad]
-    u32 npad, n;
-    // comp < ncomp: a coordinate; ncomp <= comp < DIM (padding dims of the template): 0; comp == DIM: the distance
-    template <int U>
-    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 ncomp, bool is_dis) const {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const u32 p = (cb + u) * 32 + lane;
-            v[u] = 0.0f;
-            if (p < n) {
-                if (is_dis) v[u] = __ldcg(dis + p);
-                else if (comp < ncomp) v[u] = __ldg(q + (size_t)comp * npad + p);
-            }
-        }
-    }
-    __device__ __forceinline__ void wait_ld() const {}
-    template <int U>
-    __device__ __forceinline__ void store(u32, u32 lane, u32 cb, const float (&v)[U]) const {   // distances only
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const u32 p = (cb + u) * 32 + lane;
-            if (p < n) __stcg(dis + p, v[u]);
-        }
-    }
-    __device__ __forceinline__ void wait_st() const {}
-    template <int DIM>
-    __device__ __forceinline__ void load_point(u32 p, u32, float (&r)[DIM]) const {
-#pragma unroll
-        for (int c = 0; c < DIM; ++c) r[c] = __ldg(q + (size_t)c * npad + p);
-    }
-};
-
 // point -> box squared distance (KDNode.h:105-118) without branches: the excess along a dimension is
 // max(r - hi, lo - r, 0) -- the same subtraction result the reference's if/else picks, or (+-)0
 template <int DIM>
@@ -595,30 +554,6 @@ __global__ void __launch_bounds__(512, 1) kdline_warp_kernel(WarpArgs a) {
     }
 }
 
-// the same per-cloud code over points left in global memory: every warp of the CTA takes clouds
-template <int DIM, int BPL, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) kdline_warpg_kernel(WarpArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const u32 warp = warp_id(), lane = lane_id();
-    const u32 nw = blockDim.x >> 5;
-    unsigned char *meta = smem_raw + (size_t)warp * a.meta_bytes;
-    const u32 pend = smem_u32(meta);
-    u32 *nlo_s = reinterpret_cast<u32 *>(meta + (size_t)a.R * a.S * ((DIM + 3) / 4) * 16);
-    u32 cloud = warp * gridDim.x + blockIdx.x;
-    while (cloud < a.B) {
-        unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
-        GlobalStoreT<(MAXT == 256 && DIM <= 4)> st;
-        st.q = reinterpret_cast<const float *>(rg);
-        st.dis = reinterpret_cast<float *>(rg) + (size_t)a.dim * a.npad;
-        st.npad = a.npad;
-        st.n = a.n;
-        warp_cloud<DIM, BPL>(a, st, cloud, nlo_s, pend);
-        u32 nxt = 0;
-        if (lane == 0) nxt = atomicAdd(a.counter, 1u);
-        cloud = __shfl_sync(FULL, nxt, 0) + nw * gridDim.x;
-    }
-}
-
 // ======================================================================================================
 //  host side
 // ======================================================================================================
@@ -626,17 +561,15 @@ static int warp_dim(int dim) { return dim <= 2 ? 2 : dim == 3 ? 3 : dim == 4 ? 4
 
 bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpPlan *pl) {
     if (dim == 0 || dim > 7 || h == 0 || h > 7 || n == 0 || B == 0) return false;
-    if (const char *e = getenv("FPS_B200_WARP"))
-        if (atoi(e) == 0) return false;
+    const Tuning &tu = tuning();
+    if (tu.warp == 0) return false;
     const size_t S = (size_t)1 << h;
     const int dimp = warp_dim((int)dim);
     const size_t nch = (((n + 31) / 32) + W_U - 1) / W_U * W_U;
     const size_t slot = (size_t)(dimp + 1) * 32 * (nch + 4) * 4;
     u32 tm = ((size_t)(dimp + 1) * nch <= W_TMEM_COLS) ? 4u : 0u;
-    if (const char *e = getenv("FPS_B200_WARP_TMEM"))
-        if (atoi(e) == 0) tm = 0;
-    bool lazy = true;
-    if (const char *e = getenv("FPS_B200_WARP_LAZY")) lazy = atoi(e) != 0;
+    if (tu.warp_tmem == 0) tm = 0;
+    const bool lazy = tu.warp_lazy != 0;
     const size_t cap = 227 * 1024 - 64;
     const size_t pr = (size_t)((dimp + 3) / 4) * 16;
     auto meta_of = [&](size_t R) { return (R * S * pr + (S + 1) * 4 + 15) & ~(size_t)15; };
@@ -653,8 +586,7 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
         while (hw < 4 && (hw + 1) * (meta_of(Rmin) + cslot) <= cap) ++hw;
         // measured on cfg 3 (64 x 16384 x 3 -> 4096, h=7): 6.7 ms against 5.8 ms for the async cluster kernel (4 buckets
         // per lane + TMEM round trips make the lone warp's pick ~2900 cycles), so it is opt-in: FPS_B200_WARP_HYBRID=1
-        bool hyb = false;
-        if (const char *e = getenv("FPS_B200_WARP_HYBRID")) hyb = hw > 0 && atoi(e) != 0;
+        const bool hyb = hw > 0 && tu.warp_hybrid == 1;
         if (hyb) {
             size_t R = Rmin;
             while (lazy && R < W_MAXR && hw * (meta_of(R + 1) + cslot) <= cap) ++R;
@@ -669,46 +601,13 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
             pl->grid = (u32)grid;
             pl->lazy = lazy ? 1 : 0;
             pl->nch = (u32)nch;
-            pl->global = 0;
             pl->hybrid = 1;
             pl->smem = hw * (meta_of(R) + cslot);
             if (pl->smem < 120 * 1024) pl->smem = 120 * 1024;
             return true;
         }
     }
-    if (sw + tm == 0) {
-        // not on chip: points stay in global memory, one warp per cloud, worth it only when the batch keeps every SM
-        // busy with many clouds (throughput from clouds in flight, HBM-bound); small batches go to the cluster kernels
-        size_t minB = (size_t)2 * n_sms;   // ~2 clouds per SM: where it overtakes 16-CTA groups on 100 k-point clouds (scripts/cmp_cfg5.py)
-        if (const char *e = getenv("FPS_B200_WARP_GLOBAL_MINB")) minB = (size_t)atol(e);
-        if (B < minB) return false;
-        // long pending lists matter more than warps per SM here: every early flush re-reads a bucket from HBM, and in
-        // 6-D the reference itself defers ~14 samples per pick.  Warps per CTA = what the lists
-        // leave room for (at least 4: each warp keeps (D+1) x 8 lines in flight).
-        // many clouds per SM: 16 warps per CTA with 8-chunk blocks; fewer (an 8-GPU shard of cfg 5 is 3.5 per SM): 8 warps
-        // with 16-chunk blocks -- twice the bytes in flight per warp (512 x 100 k: 81.8 -> 60.7 ms; 4096: 224 vs 269 ms)
-        const u32 maxt = (dimp <= 4 && B > (size_t)8 * n_sms) ? 512 : 256;   // up to one wave of 8-warp CTAs
-        size_t R = lazy ? (dimp <= 4 ? 6 : W_MAXR) : 1;
-        size_t nwg = maxt / 32;
-        while (nwg > 4 && nwg * meta_of(R) > cap) --nwg;
-        while (R > Rmin && nwg * meta_of(R) > cap) --R;
-        if (nwg * meta_of(R) > cap) return false;
-        pl->dimp = dimp;
-        pl->rs = (u32)R;
-        pl->bpl = S <= 32 ? 1 : 4;
-        pl->n_tmem_warps = 0;
-        pl->n_smem_warps = (u32)nwg;
-        pl->slot_bytes = 0;
-        pl->meta_bytes = (u32)meta_of(R);
-        pl->lazy = lazy ? 1 : 0;
-        pl->nch = (u32)nch;
-        pl->global = 1;
-        pl->hybrid = 0;
-        pl->smem = nwg * meta_of(R);
-        const size_t gmax = (size_t)n_sms;   // spread over every SM before stacking warps
-        pl->grid = (u32)(B < gmax ? B : gmax);
-        return true;
-    }
+    if (sw + tm == 0) return false;   // not on chip: the streaming sampler (kdline_stream.cu) or the cluster / grid kernels take it
     const size_t nw = sw + tm;
     size_t R = Rmin;
     while (lazy && R < W_MAXR && nw * meta_of(R + 1) + sw * slot <= cap) ++R;
@@ -725,7 +624,6 @@ bool plan_kdline_warp(size_t n, size_t dim, size_t h, size_t B, int n_sms, WarpP
     pl->grid = (u32)grid;
     pl->lazy = lazy ? 1 : 0;
     pl->nch = (u32)nch;
-    pl->global = 0;
     pl->smem = nw * meta_of(R) + sw * slot;
     // tensor memory is allocated whole: never let a second CTA of this kernel become resident on the SM
     if (tm && pl->smem < 120 * 1024) pl->smem = 120 * 1024;
@@ -738,15 +636,6 @@ static cudaError_t launch_warp_t(const WarpPlan &pl, const WarpArgs &a, cudaStre
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     kern<<<pl.grid, 32 * (pl.n_tmem_warps + pl.n_smem_warps), pl.smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-template <int DIM, int BPL, int MAXT>
-static cudaError_t launch_warpg_t(const WarpPlan &pl, const WarpArgs &a, cudaStream_t st) {
-    auto kern = kdline_warpg_kernel<DIM, BPL, MAXT>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
-    if (e != cudaSuccess) return e;
-    kern<<<pl.grid, 32 * pl.n_smem_warps, pl.smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -779,21 +668,6 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;
-    if (pl.global) {
-        const bool wide = pl.n_smem_warps <= 8;   // the plan's CTA size picks the variant
-        switch (pl.dimp) {
-            case 2: e = wide ? (b1 ? launch_warpg_t<2, 1, 256>(pl, a, st) : launch_warpg_t<2, 4, 256>(pl, a, st))
-                         : (b1 ? launch_warpg_t<2, 1, 512>(pl, a, st) : launch_warpg_t<2, 4, 512>(pl, a, st)); break;
-            case 3: e = wide ? (b1 ? launch_warpg_t<3, 1, 256>(pl, a, st) : launch_warpg_t<3, 4, 256>(pl, a, st))
-                         : (b1 ? launch_warpg_t<3, 1, 512>(pl, a, st) : launch_warpg_t<3, 4, 512>(pl, a, st)); break;
-            case 4: e = wide ? (b1 ? launch_warpg_t<4, 1, 256>(pl, a, st) : launch_warpg_t<4, 4, 256>(pl, a, st))
-                         : (b1 ? launch_warpg_t<4, 1, 512>(pl, a, st) : launch_warpg_t<4, 4, 512>(pl, a, st)); break;
-            case 6: e = b1 ? launch_warpg_t<6, 1, 256>(pl, a, st) : launch_warpg_t<6, 4, 256>(pl, a, st); break;
-            default: e = b1 ? launch_warpg_t<7, 1, 256>(pl, a, st) : launch_warpg_t<7, 4, 256>(pl, a, st); break;
-        }
-        count_launch();
-        return e;
-    }
     switch (pl.dimp) {
         case 2: e = b1 ? launch_warp_t<2, 1>(pl, a, st) : launch_warp_t<2, 4>(pl, a, st); break;
         case 3: e = b1 ? launch_warp_t<3, 1>(pl, a, st) : launch_warp_t<3, 4>(pl, a, st); break;

@@ -360,8 +360,7 @@ static cudaError_t ks_occupancy_d(bool big, size_t smem, int *occ) {
 
 bool plan_kdsmall(size_t n, size_t dim, size_t h, size_t B, int n_sms, KdSmallPlan *pl) {
     if (dim == 0 || dim > 8 || n == 0 || n > 65535 || h == 0 || h > 8 || B == 0) return false;
-    if (const char *e = getenv("FPS_B200_KDSMALL"))
-        if (atoi(e) == 0) return false;
+    if (tuning().kdsmall == 0) return false;
     size_t smem = ks_smem_bytes(n, dim, h, false, 8);
     bool big = false;
     if (smem > 110 * 1024) {   // fewer than two clouds per SM: one CTA of 1024 threads per SM, index arrays in global memory

@@ -12,8 +12,10 @@
  *   - indices out are size_t / uint64 (src/lib.cpp:240-245, 561-562), [k] or [B][k].
  *   - return 0 on success.  1 and 2 keep the reference's meaning (src/wrapper.hpp:121-127).
  *   - host-pointer entry points are synchronous and re-entrant; device memory, streams and
- *     workspaces are private to the library.  `points` may also be a DEVICE pointer (the clouds are then
- *     sampled on the device they live on, without an upload, after a device synchronise); page-locked
+ *     workspaces are private to the library; the caller's current device is left as it was.  Single-cloud
+ *     entries run on the caller's current device.  `points` may also be a DEVICE pointer (the clouds are then
+ *     sampled on the device they live on, without an upload, ordered behind the producer's stream by an
+ *     event -- fps_b200_set_producer_stream; no device-wide synchronisation); page-locked
  *     buffers make the host path faster (pipelined upload, indices written straight into `out`).  *_dev entry points take device pointers and a CUDA
  *     stream (void* == cudaStream_t) and only enqueue work.
  *   - there is NO CPU fallback: without a usable sm_100 device the calls fail with FPS_ERR_NO_DEVICE.
@@ -41,6 +43,7 @@ extern "C" {
 #define FPS_ERR_NO_DEVICE 4  /* no CUDA device / not an sm_100 part                                */
 #define FPS_ERR_WORKSPACE 5  /* *_dev: workspace too small or misaligned                           */
 #define FPS_ERR_UNSUPPORTED 6/* shape outside what the kernels cover               */
+#define FPS_ERR_NCCL 7       /* NCCL missing / no communicator / a collective failed                  */
 #define FPS_ERR_CUDA 100     /* 100 + cudaError_t of the failing runtime call                      */
 
 #define FPS_B200_MAX_KDLINE_DIM 8 /* BUCKET_FPS_MAX_DIM, src/wrapper.hpp:8-11 */
@@ -56,7 +59,13 @@ FPS_API int fps_b200_vanilla(const float *points, size_t n, size_t dim, size_t k
 
 /* QuickFPS kd-line.  SAME NAME AND SIGNATURE as the reference's C ABI (src/wrapper.hpp:118-132), so a
  * build of the reference can link this library in place of wrapper.hpp.  start_idx addresses the
- * POSITION in the array after the kd build permuted it (src/wrapper.hpp:54-55). */
+ * POSITION in the array after the kd build permuted it (src/wrapper.hpp:54-55).
+ *
+ * One restriction the reference does not have: the build keeps 2^height bucket slots, so heights with 2^height > 2 * n_points
+ * (beyond height 6) and heights above 24 return FPS_ERR_UNSUPPORTED (6).  The reference's python front-end asserts
+ * 2^height <= n_points (src/fpsample/__init__.py:197), so this is only reachable through the C ABI or under `python -O`.
+ * (Clamping the height instead would NOT be exact: the mean split is unbalanced, a leaf at the clamped depth can still hold
+ * several points that the reference would keep partitioning.) */
 FPS_API int bucket_fps_kdline(const float *raw_data, size_t n_points, size_t dim, size_t n_samples,
                       size_t start_idx, size_t height, size_t *sampled_point_indices);
 
@@ -89,6 +98,31 @@ FPS_API int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_sa
                   size_t *out_indices);
 FPS_API int fps_b200_npdu_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t window,
                         const size_t *start, size_t *out_indices, const int *devices, int n_devices);
+
+/* ---- multi-GPU: shards on every GPU, indices gathered to rank 0 over NCCL (new) ----------------------
+ * Clouds are independent: a batch of n_clouds is cut into contiguous shards (remainder to the low ranks, the rule of the
+ * *_batch entries), every GPU samples its shard with NO inter-GPU traffic, and the only exchange is the gather of the index
+ * arrays to rank 0 (uint32 on the wire, grouped ncclSend / ncclRecv over NVLink, widened on rank 0's device, one copy to the
+ * host).  NCCL is bound at run time (dlopen libnccl.so.2); without it these entries return FPS_ERR_NCCL.
+ *   one process per GPU : rank 0 calls fps_b200_comm_unique_id, the 128 bytes reach every rank through the launcher's
+ *                         rendezvous, every rank calls fps_b200_comm_init on its (current) device.
+ *   one process, G GPUs : fps_b200_comm_init_local(devices, G)   (ncclCommInitAll, one communicator + stream per device). */
+#define FPS_COMM_ID_BYTES 128
+FPS_API int fps_b200_comm_unique_id(void *id128);
+FPS_API int fps_b200_comm_init(const void *id128, int n_ranks, int rank);
+FPS_API int fps_b200_comm_init_local(const int *devices, int n_devices);
+FPS_API void fps_b200_comm_destroy(void);
+FPS_API int fps_b200_comm_ranks(void);    /* 0 = no communicator */
+FPS_API int fps_b200_nccl_version(void);  /* e.g. 22809; 0 = NCCL not found */
+/* Collective.  One process per GPU: `points` / `start` are THIS RANK's shard ([nb][n][dim], nb = its share of n_clouds; host or
+ * device memory).  One process with several endpoints: the whole batch [n_clouds][n][dim] in host memory.  The indices of
+ * all n_clouds clouds arrive in out_rank0 ([n_clouds][k], host memory) where rank 0 lives; other ranks pass NULL. */
+FPS_API int fps_b200_kdline_batch_sharded(const float *points, size_t n_clouds, size_t n, size_t dim, size_t k,
+                                  const size_t *start, size_t height, size_t *out_rank0);
+FPS_API int fps_b200_vanilla_batch_sharded(const float *points, size_t n_clouds, size_t n, size_t dim, size_t k,
+                                   const size_t *start, size_t *out_rank0);
+/* Collective: gather index arrays that were sampled separately (local = this rank's [nb][k] uint64, host or device). */
+FPS_API int fps_b200_gather_indices(const uint64_t *local, size_t nb, size_t k, size_t n_clouds, uint64_t *out_rank0);
 
 /* ---- batches, device pointers (inputs already resident in HBM) ---------------------------------- */
 
@@ -133,7 +167,23 @@ FPS_API const char *fps_b200_version(void);
 FPS_API const char *fps_b200_last_error(void);      /* thread-local description of the last failure           */
 FPS_API uint64_t fps_b200_kernel_launches(void);    /* kernels launched by this library in this process       */
 FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kernel/shape the last call picked  */
-FPS_API int fps_b200_debug_counters(uint64_t *out16); /* phase counters of the last kd-line cluster launch (diagnostics) */
+/* diagnostics: phase / executed-work counters of the last launch of one sampler family (16 words, meaning per family in
+ * fpsample_b200/capi.py); the kernels only count when the library is built with -DFPS_COUNTERS=1 (bench.py's W_exec). */
+#define FPS_DBG_ASYNC 0
+#define FPS_DBG_WARP 1
+#define FPS_DBG_BUILD 2
+#define FPS_DBG_GRID 3
+#define FPS_DBG_STREAM 4 /* executed work of the streaming sampler (tuning knob COUNT=1): points scanned, point-updates,
+                          bucket passes, early passes (full pending list), bucket tests, picks, clouds */
+FPS_API int fps_b200_debug_counters(int which, uint64_t *out16);
+/* Planner overrides (tests, experiments).  The library reads FPS_B200_<NAME> from the environment ONCE, at first use; after
+ * that only this call changes a knob.  value -1 = the planner's own choice.  Names: GRID, GROUP, GRIDBUILD, VANILLA_KD, PIPE,
+ * ZEROCOPY, GRID_ECAP, WARP, WARP_TMEM, WARP_LAZY, WARP_HYBRID, WARP_GLOBAL_MINB, KDSMALL, STREAM_WARPS, COUNT. */
+FPS_API int fps_b200_set_tuning(const char *name, long value);
+/* Device-resident inputs of the host-pointer entries: the calling thread's NEXT call waits (on the device, through an event)
+ * for the work queued on `stream` -- the stream that produced the points -- instead of the legacy default stream.  Nothing is
+ * synchronised device-wide. */
+FPS_API void fps_b200_set_producer_stream(void *stream);
 /* Phase timing of the *_dev entries (measurement only, off by default): when enabled, the calling thread's next
  * *_dev call records CUDA events on its stream around the kd build launches and the sampling launch;
  * fps_b200_last_phase_ms waits for them and returns both durations (build = 0 for the vanilla entry). */

@@ -1,0 +1,4 @@
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:kdline_stream -c 1 -f -o gpurun_out/r02_ncu_stream2_d3_512_wpc4 python scripts/cmp_cfg5.py 3 512 --wpc=4 --check=0 > gpurun_out/r2e_ncu512.log 2>&1
+tail -2 gpurun_out/r2e_ncu512.log
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:kdline_stream -c 1 -f -o gpurun_out/r02_ncu_stream2_d3_4096_wpc4 python scripts/cmp_cfg5.py 3 4096 --wpc=4 --check=0 > gpurun_out/r2e_ncu4096.log 2>&1
+tail -2 gpurun_out/r2e_ncu4096.log

@@ -10,7 +10,7 @@ for B in [int(x) for x in sys.argv[2:]] or [512]:
     dp = torch.from_numpy(host).cuda(); do = torch.empty((B, k), dtype=torch.int64, device="cuda")
     res = {}
     for name, env in (("cta build", "0"), ("grid build", "1")):
-        os.environ["FPS_B200_GRIDBUILD"] = env
+        capi.set_tuning("GRIDBUILD", int(env))
         wsb = capi.workspace_bytes(capi.ALGO_KDLINE, B, n, d, k, h); ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda"); wp = (ws.data_ptr() + 255) & ~255
         capi.phase_timing(True); best = None
         for _ in range(3):

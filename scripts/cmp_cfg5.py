@@ -1,32 +1,42 @@
-"""cfg5-shaped batches (100k points -> 8192, h=7) at the per-GPU batch sizes of an 8-GPU shard: grouped grid sampler
-(planner default below 4 clouds per SM) against the one-warp-per-cloud streaming kernel; build / sampling split."""
+"""cfg5-shaped batches (100k points -> 8192, h=7): the streaming sampler with 1 / 2 / 4 warps per cloud at the per-GPU batch
+sizes of a 1..8-GPU split; build / sampling split, executed-work counters, a few clouds checked against the oracle.
+usage: python scripts/cmp_cfg5.py D B [B ...] [--wpc 1,2,4] [--check N]"""
 import os, sys
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from fpsample_b200 import capi, synth
-n, d, k, h = 100000, int(sys.argv[1]) if len(sys.argv) > 1 else 3, 8192, 7
-Bs = [int(x) for x in sys.argv[2:]] or [148, 296, 512]
-base = np.stack([synth.uniform(3000 + b, n, d) for b in range(16)])
+from oracle import oracle as O
+args = [x for x in sys.argv[1:] if not x.startswith("--")]
+opt = dict(x[2:].split("=") for x in sys.argv[1:] if x.startswith("--"))
+n, d, k, h = 100000, int(args[0]) if args else 3, 8192, 7
+Bs = [int(x) for x in args[1:]] or [512]
+wpcs = [int(x) for x in opt.get("wpc", "-1").split(",")]
+ncheck = int(opt.get("check", "2"))
+nreal = 32
+base = np.stack([synth.uniform(3000 + b, n, d) for b in range(nreal)])
+want = {b: O.kdline(base[b], k, h, 0) for b in range(ncheck)}
 for B in Bs:
-    host = np.concatenate([base] * ((B + 15) // 16))[:B]
-    host = host + (np.arange(B, dtype=np.float32) * 1e-3)[:, None, None]
+    host = np.concatenate([base] * ((B + nreal - 1) // nreal))[:B]
     dp = torch.from_numpy(host).cuda(); do = torch.empty((B, k), dtype=torch.int64, device="cuda")
-    res = {}
-    for name, env in (("default", {}), ("warpg", {"FPS_B200_WARP_GLOBAL_MINB": "1", "FPS_B200_GROUP": "0"})):
-        for kk in ("FPS_B200_WARP_GLOBAL_MINB", "FPS_B200_GROUP"): os.environ.pop(kk, None)
-        os.environ.update(env)
+    for wpc in wpcs:
+        capi.set_tuning("STREAM_WARPS", wpc); capi.set_tuning("WARP_GLOBAL_MINB", 1); capi.set_tuning("GROUP", 0)
         wsb = capi.workspace_bytes(capi.ALGO_KDLINE, B, n, d, k, h); ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda"); wp = (ws.data_ptr() + 255) & ~255
-        capi.phase_timing(True)
-        best = None
-        for _ in range(3):
-            capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, do.data_ptr(), wp, wsb, torch.cuda.current_stream().cuda_stream)
+        st = torch.cuda.current_stream().cuda_stream
+        capi.phase_timing(True); best = None
+        for _ in range(2):
+            capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, do.data_ptr(), wp, wsb, st)
             ph = capi.last_phase_ms()
             if best is None or sum(ph) < sum(best): best = ph
         capi.phase_timing(False)
-        res[name] = (best, do.cpu().numpy().copy(), capi.last_plan())
+        capi.set_tuning("COUNT", 1)
+        capi.kdline_batch_dev(dp.data_ptr(), B, n, d, k, 0, h, do.data_ptr(), wp, wsb, st)
+        cnt = capi.debug_counters(capi.DBG_STREAM)
+        capi.set_tuning("COUNT", -1)
+        got = do.cpu().numpy().astype(np.uint64)
+        ok = all(np.array_equal(got[b + nreal * j], want[b]) for b in want for j in range((B - b + nreal - 1) // nreal) if b + nreal * j < B)
+        pts, pu, fl, early, tests, picks, clouds = [int(x) for x in cnt[:7]]
+        byt = pts * 4 * (d + 2)
+        print(f"B={B} d={d} wpc={wpc}: build {best[0]:7.2f} ms sampling {best[1]:7.2f} ms -> {B / sum(best) * 1e3:7.0f} clouds/s | parity {'OK' if ok else 'MISMATCH'} | "
+              f"per pick: {pts / max(picks, 1):.0f} pts scanned, {pu / max(picks, 1):.0f} point-updates, {fl / max(picks, 1):.2f} passes ({early / max(picks, 1):.2f} early) | "
+              f"{byt / 1e9:.1f} GB algorithmic -> {byt / best[1] / 1e6:.0f} GB/s | {capi.last_plan().split(' + ')[-1][:110]}", flush=True)
         del ws
-    same = np.array_equal(res["default"][1], res["warpg"][1])
-    for name in res:
-        b, _, plan = res[name]
-        print(f"B={B} d={d} {name:8s}: build {b[0]:8.2f} ms sampling {b[1]:8.2f} ms -> {B / (b[0] + b[1]) * 1e3:8.0f} clouds/s | {plan[:150]}")
-    print("   same indices:", same)

@@ -11,7 +11,7 @@ for B, n, d, k, h in shapes:
     do = torch.empty((B, k), dtype=torch.int64, device="cuda")
     res = []
     for mode in ("0", "1"):
-        os.environ["FPS_B200_GROUP"] = mode
+        capi.set_tuning("GROUP", int(mode))
         wsb = capi.workspace_bytes(capi.ALGO_KDLINE, B, n, d, k, h)
         ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda")
         wp = (ws.data_ptr() + 255) & ~255

@@ -13,7 +13,7 @@ for B, n, d, k in shapes:
     for mode in ("0", "1"):
         if mode == "0" and n * k > 3e10:
             res.append((float("nan"), "skipped (minutes)", None)); continue
-        os.environ["FPS_B200_VANILLA_KD"] = mode
+        capi.set_tuning("VANILLA_KD", int(mode))
         wsb = capi.workspace_bytes(capi.ALGO_VANILLA, B, n, d, k, 0)
         ws = torch.empty(wsb + 512, dtype=torch.uint8, device="cuda")
         wp = (ws.data_ptr() + 255) & ~255

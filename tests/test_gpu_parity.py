@@ -114,54 +114,48 @@ def test_tie_clouds(seed, oracle):
 
 @pytest.mark.parametrize("n,d,levels,k,h,s", [(60000, 3, 24, 3000, 6, 5), (40000, 2, 40, 2500, 8, 0), (30000, 6, 3, 1500, 7, 9),
                                               (70000, 1, 5000, 2000, 5, 1), (20000, 3, 2, 500, 10, 0)])
-def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle, monkeypatch):
+def test_async_cluster_path_on_tie_lattices(n, d, levels, k, h, s, oracle):
     """clouds too big for one SM go through the coordinator/worker cluster kernel (the planner now prefers the grouped
     grid sampler for them: switched off here): ties, duplicates and near-empty buckets must not disturb its
     upper-bound logic."""
-    monkeypatch.setenv("FPS_B200_GROUP", "0")
     g = synth.grid_ties(n + h, n, d, levels=levels)
-    got = capi.kdline(g, k, h, s)
-    assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warpg_kernel")), capi.last_plan()
+    with capi.tuning(group=0):
+        got = capi.kdline(g, k, h, s)
+    assert any(x in capi.last_plan() for x in ("kdline_async_kernel", "kdline_stream_kernel")), capi.last_plan()
     np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
-    monkeypatch.delenv("FPS_B200_GROUP")
     got = capi.kdline(g, k, h, s)   # and the default route
     np.testing.assert_array_equal(got, oracle.kdline(g, k, h, s), err_msg=capi.last_plan())
 
 
-def test_async_batches_and_cluster_sizes(oracle, monkeypatch):
-    monkeypatch.setenv("FPS_B200_GROUP", "0")
+def test_async_batches_and_cluster_sizes(oracle):
     for B, n, k, h in [(3, 30000, 800, 7), (20, 20000, 400, 6), (80, 16384, 300, 7), (160, 14000, 200, 5)]:
         pcs = synth.uniform_batch(8000 + B, B, n, 3)
         st = (np.arange(B) * 7) % n
-        got = capi.kdline_batch(pcs, k, h, st, devices=[0])
-        assert any(x in capi.last_plan() for x in ("kdline_dist_kernel", "kdline_async_kernel", "kdline_warp")), capi.last_plan()
+        with capi.tuning(group=0):
+            got = capi.kdline_batch(pcs, k, h, st, devices=[0])
+        assert any(x in capi.last_plan() for x in ("kdline_async_kernel", "kdline_warp", "kdline_stream")), capi.last_plan()
         want = np.stack([oracle.kdline(pcs[b], k, h, int(st[b])) for b in range(B)])
         np.testing.assert_array_equal(got, want, err_msg=capi.last_plan())
 
 
-@pytest.mark.parametrize("env", [{"FPS_B200_WARP_GLOBAL_MINB": "1"}, {"FPS_B200_DIST": "1"}, {"FPS_B200_WARP_LAZY": "0"},
-                                 {"FPS_B200_WARP_TMEM": "0"}, {"FPS_B200_WARP_HYBRID": "1"}])
-def test_alternative_samplers(env, oracle):
-    """every kd-line sampler must give the reference's indices, not only the one the planner prefers: the
-    one-warp-per-cloud kernel over global memory (big batches), the distributed-bucket cluster kernel (opt-in),
-    the eager variant of the warp kernel and its shared-memory-only placement."""
-    env = dict(env, FPS_B200_GROUP="0")   # the planner's default for medium clouds is the grouped grid sampler: off here
-    os.environ.update(env)
-    try:
-        want_plan = {"FPS_B200_WARP_GLOBAL_MINB": "kdline_warpg_kernel", "FPS_B200_DIST": "kdline_dist_kernel",
-                     "FPS_B200_WARP_LAZY": "eager", "FPS_B200_WARP_TMEM": "tmem 0", "FPS_B200_WARP_HYBRID": "hybrid"}[next(iter(env))]
-        big = next(iter(env)) in ("FPS_B200_WARP_GLOBAL_MINB", "FPS_B200_DIST")
-        if next(iter(env)) == "FPS_B200_WARP_HYBRID":   # only clouds between the shared-memory and the TMEM limit
-            for n, d, k, h, s, gen in [(16384, 3, 700, 7, 11, "u"), (15500, 3, 300, 5, 2, "g"), (16000, 3, 400, 6, 0, "l")]:
-                pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=37),
-                      "l": lambda: synth.lidar(n, n)}[gen]()
-                got = capi.kdline(pc, k, h, s)
-                assert want_plan in capi.last_plan(), capi.last_plan()
-                np.testing.assert_array_equal(got, oracle.kdline(pc, k, h, s), err_msg=capi.last_plan())
-            return
-        shapes = [(30000, 3, 900, 7, 5, "u"), (20000, 6, 500, 6, 0, "u"), (40000, 2, 800, 5, 3, "g"), (50000, 1, 700, 5, 1, "g"),
-                  (25000, 3, 600, 7, 2, "l")] if big else \
-                 [(4096, 3, 1024, 5, 0, "u"), (3000, 6, 500, 5, 7, "u"), (5000, 2, 700, 7, 1, "g"), (4096, 3, 600, 6, 9, "l")]
+@pytest.mark.parametrize("knobs", [dict(warp_global_minb=1), dict(warp_global_minb=1, stream_warps=1), dict(warp_global_minb=1, stream_warps=2),
+                                   dict(warp_lazy=0), dict(warp_tmem=0), dict(warp_hybrid=1)],
+                         ids=["stream", "stream-1warp", "stream-2warps", "eager", "no-tmem", "hybrid"])
+def test_alternative_samplers(knobs, oracle):
+    """every kd-line sampler must give the reference's indices, not only the one the planner prefers: the streaming
+    kernel over global memory with 1, 2 and 4 warps per cloud (big batches of big clouds), the eager variant of the on-chip
+    warp kernel, its shared-memory-only placement and the shared-memory + TMEM hybrid."""
+    first = next(iter(knobs))
+    want_plan = {"warp_global_minb": "kdline_stream_kernel", "warp_lazy": "eager", "warp_tmem": "tmem 0", "warp_hybrid": "hybrid"}[first]
+    big = first == "warp_global_minb"
+    with capi.tuning(group=0, **knobs):   # the planner's default for medium clouds is the grouped grid sampler: off here
+        if first == "warp_hybrid":   # only clouds between the shared-memory and the TMEM limit
+            shapes = [(16384, 3, 700, 7, 11, "u"), (15500, 3, 300, 5, 2, "g"), (16000, 3, 400, 6, 0, "l")]
+        elif big:
+            shapes = [(30000, 3, 900, 7, 5, "u"), (20000, 6, 500, 6, 0, "u"), (40000, 2, 800, 5, 3, "g"), (50000, 1, 700, 5, 1, "g"),
+                      (25000, 3, 600, 7, 2, "l"), (9000, 8, 300, 7, 4, "u"), (12345, 4, 1000, 7, 12344, "g")]
+        else:
+            shapes = [(4096, 3, 1024, 5, 0, "u"), (3000, 6, 500, 5, 7, "u"), (5000, 2, 700, 7, 1, "g"), (4096, 3, 600, 6, 9, "l")]
         for n, d, k, h, s, gen in shapes:
             pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=37),
                   "l": lambda: synth.lidar(n, n)}[gen]()
@@ -173,9 +167,6 @@ def test_alternative_samplers(env, oracle):
             got = capi.kdline_batch(pcs, 300, 7, np.arange(12) * 3, devices=[0])
             assert want_plan in capi.last_plan(), capi.last_plan()
             np.testing.assert_array_equal(got, np.stack([oracle.kdline(pcs[b], 300, 7, 3 * b) for b in range(12)]))
-    finally:
-        for k_ in env:
-            os.environ.pop(k_, None)
 
 
 @pytest.mark.parametrize("n,d,k,h,s,gen", [(300000, 3, 5000, 9, 0, "u"), (270001, 3, 3000, 8, 77, "l"), (150000, 3, 150000, 7, 3, "g"),
@@ -185,8 +176,7 @@ def test_grid_sampler(n, d, k, h, s, gen, oracle):
     """the whole-GPU sampler for one huge cloud (kdline_grid_kernel: points in shared memory, a batch of picks per
     grid-wide exchange) forced onto smaller clouds too: ties, duplicates (k = n drives every distance to 0), odd
     sizes, every padded dimension."""
-    os.environ["FPS_B200_GRID"] = "1"
-    try:
+    with capi.tuning(grid=1):
         pc = {"u": lambda: synth.uniform(n + d, n, d), "g": lambda: synth.grid_ties(n, n, d, levels=23),
               "l": lambda: synth.lidar(n, n)}[gen]()
         got = capi.kdline(pc, k, h, s)
@@ -198,8 +188,6 @@ def test_grid_sampler(n, d, k, h, s, gen, oracle):
             assert "kdline_grid_kernel" in capi.last_plan(), capi.last_plan()
             for b in range(3):
                 np.testing.assert_array_equal(gb[b], oracle.kdline(pcs[b], min(k, 500), h, [s, 0, 1][b]))
-    finally:
-        os.environ.pop("FPS_B200_GRID", None)
 
 
 @pytest.mark.parametrize("n,d,k,s,gen", [(4096, 3, 1024, 0, "u"), (50000, 3, 3000, 17, "l"), (3000, 2, 3000, 5, "g"), (7777, 6, 900, 3, "u"),
@@ -236,8 +224,7 @@ def test_kdtree_batch_and_python_api(oracle):
 def test_group_sampler(n, d, k, h, s, gen, B, oracle):
     """batches of medium clouds on groups of CTAs (kdline_grid_kernel, flat mode: every warp publishes its own keys,
     slices = kd subtrees): more clouds than groups, ties, duplicates, every padded dimension."""
-    os.environ["FPS_B200_GROUP"] = "1"
-    try:
+    with capi.tuning(group=1):
         mk = {"u": lambda i: synth.uniform(n + d + i, n, d), "g": lambda i: synth.grid_ties(n + i, n, d, levels=23),
               "l": lambda i: synth.lidar(n + i, n)}[gen]
         pcs = np.stack([mk(i) for i in range(B)])
@@ -246,8 +233,6 @@ def test_group_sampler(n, d, k, h, s, gen, B, oracle):
         assert "kdline_grid_kernel" in capi.last_plan() and "flat" in capi.last_plan(), capi.last_plan()
         for b in sorted({0, B // 2, B - 1}):
             np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, int(st[b])), err_msg=f"cloud {b}: {capi.last_plan()}")
-    finally:
-        os.environ.pop("FPS_B200_GROUP", None)
 
 
 @pytest.mark.parametrize("n,d,k,starts,gen", [(20000, 3, 700, [5, 1, 9], "g"), (16384, 2, 5000, [16383], "g"), (70000, 1, 2000, [0], "g"),
@@ -265,12 +250,9 @@ def test_vanilla_kd_route(n, d, k, starts, gen, oracle):
     else:
         ok, where = oracle.certify_vanilla(pc, got, n_forced=len(starts))
         assert ok, f"first bad round {where} ({capi.last_plan()})"
-    os.environ["FPS_B200_VANILLA_KD"] = "0"   # and the brute-force kernels still agree
-    try:
+    with capi.tuning(vanilla_kd=0):   # and the brute-force kernels still agree
         np.testing.assert_array_equal(capi.vanilla(pc, min(k, 300), starts), got[:min(k, 300)])
         assert "kd permutation" not in capi.last_plan()
-    finally:
-        os.environ.pop("FPS_B200_VANILLA_KD", None)
 
 
 def test_vanilla_kd_batch_with_starts(oracle):
