@@ -25,7 +25,7 @@ NVCC_FLAGS = [
     "-fmad=false", *os.environ.get("FPS_NVCC_EXTRA", "").split(),  # bit-exact parity: no FMA contraction anywhere (the kernels also use *_rn)
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
-CU = ["vanilla.cu", "kdtree.cu", "kdline.cu", "kdsmall.cu", "seqsum.cu", "npdu.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_stream.cu", "kdline_grid.cu", "kdbuild.cu", "comm.cu", "capi.cu"]
+CU = ["vanilla.cu", "kdtree.cu", "kdline.cu", "kdsmall.cu", "seqsum.cu", "npdu.cu", "kdline_async.cu", "kdline_warp.cu", "kdline_stream.cu", "kdline_grid.cu", "kdbuild.cu", "comm.cu", "floors.cu", "capi.cu"]
 HDR = ["common.cuh", "kdcommon.cuh", "seqsum.cuh", "engine.h", os.path.join(ROOT, "include", "fps_b200.h")]
 
 

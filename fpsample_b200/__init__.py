@@ -38,6 +38,7 @@ try:
         _fps_sampling_batch,
         _kernel_launches,
         _last_plan,
+        _set_producer_stream,
     )
 except ImportError as e:  # pragma: no cover - build problem, never a silent fallback
     raise ImportError(
@@ -52,8 +53,9 @@ def _cuda_view(a, ndim: int):
     """(address, shape) of a GPU-resident array (anything with __cuda_array_interface__: torch, cupy, numba), else None.
 
     SURVEY.md 8(f) row 3: clouds that are already in HBM are sampled where they are.  No implicit casts or copies on
-    the device: the buffer has to be C-contiguous float32; work that produces it must be enqueued before the call (the
-    library synchronises the device before reading it).  The index array still comes back as a host numpy array.
+    the device: the buffer has to be C-contiguous float32.  Work that produces it is waited for ON THE DEVICE, through an
+    event on the producer's stream -- the interface's `stream` entry, torch's current stream for torch tensors, else the
+    legacy default stream -- never with a device-wide synchronisation.  The index array still comes back as a host array.
     """
     cai = getattr(a, "__cuda_array_interface__", None)
     if cai is None:
@@ -71,7 +73,19 @@ def _cuda_view(a, ndim: int):
             acc *= dim
         if tuple(strides) != tuple(reversed(want)):
             raise TypeError("device arrays must be C-contiguous")
+    _set_producer_stream(_producer_stream(a, cai))
     return int(cai["data"][0]), shape
+
+
+def _producer_stream(a, cai) -> int:
+    """cudaStream_t (as an int) whose queued work produces `a`; 0 = the legacy default stream"""
+    st = cai.get("stream")
+    if isinstance(st, int):
+        return st          # 1 = legacy default, 2 = per-thread default (the CUDA handle values), else a stream handle
+    if type(a).__module__.split(".")[0] == "torch":
+        import torch
+        return int(torch.cuda.current_stream(a.device).cuda_stream)
+    return 0
 
 
 def _device_single(algo: int, dv, n_samples: int, h: int, start_idx):

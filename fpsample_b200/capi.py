@@ -48,6 +48,7 @@ EXPORTS = {
     "fps_b200_set_producer_stream": (None, [ctypes.c_void_p]),
     "fps_b200_phase_timing": (None, [ctypes.c_int]),
     "fps_b200_last_phase_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "fps_b200_sync_floor": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_void_p]),
     "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fps_b200_host_free": (None, [ctypes.c_void_p]),
 }
@@ -139,6 +140,16 @@ def last_phase_ms():
     b, s = ctypes.c_float(0), ctypes.c_float(0)
     _check("fps_b200_last_phase_ms", lib().fps_b200_last_phase_ms(ctypes.byref(b), ctypes.byref(s)))
     return float(b.value), float(s.value)
+
+
+FLOOR_WARP, FLOOR_CLUSTER, FLOOR_GRID = 0, 1, 2
+
+
+def sync_floor(kind: int, ctas: int = 1, words: int = 0, group: int = 0, rounds: int = 2000) -> float:
+    """nanoseconds per empty round of a sampler's synchronisation structure (csrc/floors.cu)"""
+    ns = ctypes.c_float(0)
+    _check("fps_b200_sync_floor", lib().fps_b200_sync_floor(kind, ctas, (group << 16) | words, rounds, ctypes.byref(ns)))
+    return float(ns.value)
 
 
 def device_count() -> int:
@@ -267,6 +278,27 @@ def nccl_version() -> int:
     return int(lib().fps_b200_nccl_version())
 
 
+_root_cache = {}   # shape -> up to 3 page-locked result buffers
+
+
+def _root_out(shape):
+    """rank 0's result buffer: page-locked when the driver hands it out (the copy from the GPU then runs at PCIe speed).
+    Pinning a quarter of a gigabyte costs ~0.1 s, so a few buffers per shape are kept and one is handed out again once the
+    caller has dropped the array it got (a surviving SLICE of it does not count: keep the array itself)."""
+    import sys
+    pool = _root_cache.setdefault(tuple(shape), [])
+    for arr in pool:
+        if sys.getrefcount(arr) <= 3:   # the pool, `arr`, getrefcount's argument: nobody else holds it
+            return arr
+    try:
+        arr = pinned_empty(shape, np.uint64)
+    except MemoryError:
+        return np.empty(shape, dtype=np.uint64)
+    if len(pool) < 3:
+        pool.append(arr)
+    return arr
+
+
 def _sharded(fn, name, pcs, n_clouds, k, start, is_root, *extra):
     """pcs: this rank's shard (one process per GPU) or the whole batch (comm_init_local); numpy array or an int device address
     with `shape`.  -> [n_clouds, k] uint64 where rank 0 lives (pinned), else None."""
@@ -277,7 +309,7 @@ def _sharded(fn, name, pcs, n_clouds, k, start, is_root, *extra):
         keep = pcs = _f32(pcs, 3)
         ptr, (b, n, d) = pcs.ctypes.data, pcs.shape
     st = _starts(start, b)
-    out = pinned_empty((n_clouds, k), np.uint64) if is_root else None
+    out = _root_out((n_clouds, k)) if is_root else None
     args = [ptr, n_clouds, n, d, k, None if st is None else st.ctypes.data] + list(extra) + [None if out is None else out.ctypes.data]
     _check(name, fn(*args))
     del keep
@@ -295,7 +327,7 @@ def vanilla_batch_sharded(pcs, n_clouds, k, start=None, is_root=True):
 def gather_indices(local, n_clouds, is_root=True):
     local = np.ascontiguousarray(local, dtype=np.uint64)
     nb, k = local.shape
-    out = pinned_empty((n_clouds, k), np.uint64) if is_root else None
+    out = _root_out((n_clouds, k)) if is_root else None
     _check("fps_b200_gather_indices", lib().fps_b200_gather_indices(local.ctypes.data, nb, k, n_clouds, None if out is None else out.ctypes.data))
     return out
 

@@ -979,7 +979,7 @@ int fps_b200_set_tuning(const char *name, long value) {
     return FPS_OK;
 }
 
-void fps_b200_set_producer_stream(void *stream) { tl_producer = static_cast<cudaStream_t>(stream); }
+void fps_b200_set_producer_stream(void *stream) { tl_producer = stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy; }
 
 void fps_b200_phase_timing(int enable) { g_phase_timing.store(enable ? 1 : 0); }
 

@@ -775,6 +775,11 @@ __global__ void __launch_bounds__(G_T, 1) kdline_grid_kernel(GridArgs a) {
 #if GDBG
     if (dbg_on)
         for (int i = 0; i < 16; ++i) g_grid_dbg[i] = dbg[i];
+#else
+    if (tid == 0 && blockIdx.x == 0) {   // rounds of group 0 over its clouds, picks they resolved (bench.py: latency roofline)
+        g_grid_dbg[0] = round;
+        g_grid_dbg[1] = (u64)((a.B + ngrp - 1) / ngrp) * (a.k - 1);
+    }
 #endif
 }
 

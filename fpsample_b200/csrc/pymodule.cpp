@@ -297,6 +297,8 @@ PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
           "Batched QuickFPS kd-line. points: B x N x C; height; start_idx: None|int|int[B]; devices: None|list[int].");
     m.def("_batch_ptr", &batch_ptr_py,
           "Batched entry over a raw float32 [B, N, D] address (device memory): algo 0 vanilla / 1 kd-line / 2 kd tree.");
+    m.def("_set_producer_stream", [](size_t stream) { fps_b200_set_producer_stream(reinterpret_cast<void *>(stream)); },
+          "The calling thread's next call with a device-resident input waits (on the device) for this cudaStream_t.");
     m.def("_device_count", []() { return fps_b200_device_count(); });
     m.def("_last_plan", []() { return std::string(fps_b200_last_plan()); });
     m.def("_kernel_launches", []() { return fps_b200_kernel_launches(); });

@@ -189,6 +189,15 @@ FPS_API void fps_b200_set_producer_stream(void *stream);
  * fps_b200_last_phase_ms waits for them and returns both durations (build = 0 for the vanilla entry). */
 FPS_API void fps_b200_phase_timing(int enable);
 FPS_API int fps_b200_last_phase_ms(float *build_ms, float *sample_ms);
+/* Latency floor of a sampler's synchronisation structure (measurement only, csrc/floors.cu): `rounds` empty rounds of the
+ * exchange the sampler performs per round, timed with CUDA events on the current device -> nanoseconds per round.
+ *   FPS_FLOOR_WARP: one warp's arg-max collectives.  FPS_FLOOR_CLUSTER: `ctas` = cluster size (512 threads per CTA).
+ *   FPS_FLOOR_GRID: `ctas` CTAs of 1024 threads, `words` = (CTAs per group << 16) | stamped 16-byte words per CTA
+ *   (group 0 = the whole grid). */
+#define FPS_FLOOR_WARP 0
+#define FPS_FLOOR_CLUSTER 1
+#define FPS_FLOOR_GRID 2
+FPS_API int fps_b200_sync_floor(int kind, int ctas, int words, int rounds, float *ns_per_round);
 FPS_API void *fps_b200_host_alloc(size_t bytes);    /* page-locked host memory for the host-pointer entries   */
 FPS_API void fps_b200_host_free(void *p);
 

@@ -529,6 +529,52 @@ def test_cfg5_batch_100k_to_8192(d, oracle, golden):
         assert oracle.certify_vanilla(pcs[b], van[b])[0], b
 
 
+@pytest.mark.parametrize("d,B,ncheck", [(3, 1200, 12), (6, 320, 4)])
+def test_cfg5_production_plan(d, B, ncheck, oracle):
+    """BASELINE.json configs[4] on the plan the full 4096-cloud batch (and every shard of it down to one eighth) takes:
+    the grid-wide build + the streaming sampler with 4 warps per cloud, 16 warps per SM.  A seeded subset of the clouds is
+    checked against the oracle, every cloud for the properties an exact FPS result has."""
+    n, k, h = 100000, 8192, 7
+    pcs = synth.uniform_batch(3000, B, n, d)
+    got = capi.kdline_batch(pcs, k, h, devices=[0])
+    plan = capi.last_plan()
+    assert "kdline_stream_kernel" in plan and "WPC=4" in plan and "gb_* grid-wide build" in plan, plan
+    for b in range(B):
+        assert got[b].max() < n
+    for b in range(0, B, 7):
+        assert len(np.unique(got[b])) == k, b
+    rng = np.random.default_rng(d)
+    for b in sorted({0, B - 1} | set(int(x) for x in rng.integers(0, B, ncheck - 2))):
+        np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, 0), err_msg=f"cloud {b}: {plan}")
+    # the shard one of eight GPUs gets takes the same kernel
+    if d == 3:
+        shard = capi.kdline_batch(pcs[:512], k, h, devices=[0])
+        assert "kdline_stream_kernel" in capi.last_plan() and "WPC=4" in capi.last_plan(), capi.last_plan()
+        np.testing.assert_array_equal(shard, got[:512])
+
+
+def test_executed_work_counters_of_the_streaming_sampler(oracle):
+    """COUNT=1: the kernel counts what it executes (bench.py's W_exec).  The reference's lazy scheme is reproduced pass for
+    pass as long as no pending list fills up, so points scanned / point-updates equal the oracle's counters."""
+    n, d, k, h, B = 30000, 3, 900, 7, 6
+    pcs = synth.uniform_batch(7700, B, n, d)
+    with capi.tuning(group=0, warp_global_minb=1, count=1):
+        got = capi.kdline_batch(pcs, k, h, devices=[0])
+        assert "kdline_stream_kernel" in capi.last_plan(), capi.last_plan()
+        cnt = capi.debug_counters(capi.DBG_STREAM)
+    pts, pu, passes, early, tests, picks, clouds = [int(x) for x in cnt[:7]]
+    assert clouds == B and picks == B * (k - 1) and tests == picks * 2**h
+    want_pu = 0
+    for b in range(B):
+        np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, 0))
+        # the reference also applies the LAST pick (KDLineTree.h:77-85), whose update nobody observes: the kernel applies
+        # samples 0 .. k-2, which is the oracle's work for k - 1 picks
+        want_pu += oracle.kdline(pcs[b], k - 1, h, 0, return_stats=True)[1]["point_updates"]
+    assert early == 0, "R=16 pending samples per bucket should never fill up on uniform 3-D clouds"
+    assert pu == want_pu, (pu, want_pu)
+    assert pts <= pu
+
+
 def test_batch_equals_single_and_per_cloud_starts(oracle):
     pcs = synth.uniform_batch(4000, 37, 4096, 3)
     st = np.arange(37) * 11
