@@ -72,7 +72,7 @@ static const KnobDesc kKnobs[] = {
     {"WARP_TMEM", nullptr, &Tuning::warp_tmem}, {"WARP_LAZY", nullptr, &Tuning::warp_lazy},
     {"WARP_HYBRID", nullptr, &Tuning::warp_hybrid}, {"WARP_GLOBAL_MINB", &Tuning::warp_global_minb, nullptr},
     {"KDSMALL", nullptr, &Tuning::kdsmall},     {"STREAM_WARPS", nullptr, &Tuning::stream_warps},
-    {"COUNT", nullptr, &Tuning::count},
+    {"COUNT", nullptr, &Tuning::count},         {"PREFETCH", nullptr, &Tuning::prefetch},
 };
 static bool set_knob(const char *name, long v) {
     for (const KnobDesc &k : kKnobs)

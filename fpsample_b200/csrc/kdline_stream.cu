@@ -22,8 +22,10 @@
 //   * a lane owns four consecutive positions of a 128-position chunk: 128-bit loads and stores, a quarter of the memory
 //     instructions and address arithmetic of a 32-bit-per-lane layout;
 //   * executed-work counters (points scanned, point-updates, flushes, tests) for the roofline (SURVEY.md 8(d) W_exec).
-// Per pick the team meets at three named barriers (bar.sync id, 32*WPC): after the tests (flush masks + pending
-// entries), after the bucket passes (per-warp partial maxima) and after the arg-max partials.
+// Per pick the team meets at two named barriers (bar.sync id, 32*WPC): after the tests (pending entries + the list of
+// buckets to pass over) and after the bucket passes (per-warp partial maxima); merging those and the arg-max over all
+// buckets are done by every warp for itself.  A bucket that is going to be passed over is prefetched into L2 with one
+// cp.async.bulk.prefetch per component the moment its owner lane decides so, before the first barrier.
 #include <cfloat>
 
 #include "common.cuh"
@@ -33,7 +35,7 @@ namespace fps {
 
 constexpr u32 S_NONE = 0xffffffffu;
 constexpr int S_U = 8;              // chunks (of 32 positions) per block of a bucket pass
-constexpr u32 S_MAXF = 8;           // flushed buckets per exchange batch
+constexpr u32 S_MAXF = 4;           // flushed buckets per exchange batch (1.3 - 2.2 per pick on the BASELINE clouds)
 constexpr u32 S_THREADS = 512;      // 16 warps per CTA, one CTA per SM (128 registers per thread)
 constexpr u32 S_REC = 48;           // bytes of a partial record: max bits, position, up to 8 coordinates
 constexpr u32 S_MAXR = 16;          // pending samples per bucket at most
@@ -46,7 +48,7 @@ struct StreamArgs {
     const u64 *starts;
     u64 *out;
     u32 *counter;       // dynamic cloud scheduler
-    u32 B, n, npad, dim, k, S, nlo_pad, R, team_bytes, count;
+    u32 B, n, npad, dim, k, S, nlo_pad, R, team_bytes, count, prefetch;
     u64 negzero;        // two binary32 -0.0 as an operand the compiler cannot see through (packed products, common.cuh)
 };
 
@@ -95,13 +97,20 @@ __device__ __forceinline__ void sts128u(u32 a, u32 x, u32 y, u32 z, u32 w) {
 }
 __device__ __forceinline__ float4 ldg128(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
+__device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   // 16-byte aligned address, size a multiple of 16
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // One cloud on a team of WPC warps.  A lane owns FOUR consecutive positions of every 128-position chunk (128-bit loads and
 // stores: a warp access is 512 contiguous bytes per component); a bucket pass is cut into runs of chunks, one run per warp.
+// Per pick the team meets at TWO named barriers: after the tests (pending entries + the list of buckets to pass over) and
+// after the passes (one partial maximum per warp and bucket).  Everything after that is done by every warp for itself --
+// merging the partial maxima into its own copy of the bucket maxima, the arg-max over them -- so no third exchange is needed.
 template <int DIM, int WPC, int BPL>
 __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 tm /* shared address */, u32 cnt_s) {
     constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
-    constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per pending-list entry
-    constexpr u32 NW = WPC * BPL;                  // flush-mask words
+    constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per pending-list entry / per max-point record
+    constexpr u32 NW = WPC * BPL;                  // 32-bucket groups: flush-mask words, table slots per lane
     constexpr int G = 2;                           // 128-position chunks per block: 8 positions per lane in registers
     const u32 lane = lane_id();
     const u32 npad = a.npad, dim = a.dim, S = a.S, k = a.k, R = a.R;
@@ -109,13 +118,14 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     const float *q = reinterpret_cast<const float *>(rg);
     float *dis = reinterpret_cast<float *>(rg) + (size_t)dim * npad;
 
-    // team shared memory (32-bit shared addresses):
-    // pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} | fmask[NW] | part[2][S_MAXF][WPC] | amax[WPC]
+    // team shared memory (32-bit shared addresses): pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} |
+    // max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted per group) | part[2][S_MAXF][WPC]
     const u32 pend = tm;
     const u32 brec = tm + R * SP * PRB;
-    const u32 fmask = brec + SP * 16;
-    const u32 part = fmask + ((NW + 3) & ~3u) * 4;
-    const u32 amax = part + 2 * S_MAXF * WPC * S_REC;
+    const u32 bmcs = brec + SP * 16;
+    const u32 fmask = bmcs + SP * PRB;
+    const u32 flist = fmask + ((NW + 3) & ~3u) * 4;
+    const u32 part = flist + SP * 4;
 
     // ---- distances start at FLT_MAX (Point.h:61-65); bucket boundaries to shared memory ------------------------------
     for (u32 p = (tw * 32 + lane) * 4; p < npad; p += WPC * 128)
@@ -128,10 +138,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         }
     }
 
-    // ---- bucket state in registers: warp tw, slot j, lane l own bucket (tw * BPL + j) * 32 + l -------------------------
+    // ---- the buckets this lane OWNS (tests, pending list): warp tw, slot j, lane l own bucket (tw * BPL + j) * 32 + l ------
     float blo[BPL][DIM], bhi[BPL][DIM], bmc[BPL][DIM], bmax[BPL];
-    u32 bpos[BPL], np[BPL];
-    u32 valid = 0;
+    u32 np[BPL];
+    // ---- every warp's own copy of ALL bucket maxima: lane l, slot s = bucket s * 32 + l ----------------------------------------
+    float tmax[NW];
+    u32 tpos[NW], tvalid = 0;
     team_sync<WPC>(team);
     {
         const float *fbox = reinterpret_cast<const float *>(rg) + (size_t)(dim + 2) * npad + a.nlo_pad;
@@ -139,13 +151,11 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         for (int j = 0; j < BPL; ++j) {
             const u32 b = (tw * BPL + j) * 32 + lane;
             bmax[j] = FLT_MAX;   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103)
-            bpos[j] = 0;
             np[j] = 0;
 #pragma unroll
             for (int c = 0; c < DIM; ++c) blo[j][c] = bhi[j][c] = bmc[j][c] = 0.0f;
             const uint4 br = lds128u(brec + b * 16);
             if (b < S && br.y > br.x) {
-                valid |= 1u << j;
 #pragma unroll
                 for (int c = 0; c < DIM; ++c)
                     if (c < (int)dim) {
@@ -153,6 +163,14 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                         bhi[j][c] = fbox[(size_t)b * 2 * dim + dim + c];
                     }
             }
+        }
+#pragma unroll
+        for (u32 s = 0; s < NW; ++s) {
+            const u32 b = s * 32 + lane;
+            const uint4 br = lds128u(brec + b * 16);
+            tmax[s] = 0.0f;
+            tpos[s] = S_NONE;
+            if (b < S && br.y > br.x) tvalid |= 1u << s;
         }
     }
 
@@ -165,11 +183,11 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     u32 bp = 0;        // parity of the partial-record buffer
 
     for (u32 t = 1; t < k; ++t) {
-        // ---- 1. every bucket against the new sample: drop / defer / flush (KDNode.h:120-146) ------------------------------
+        // ---- 1. every owned bucket against the new sample: drop / defer / flush (KDNode.h:120-146) ---------------------------
 #pragma unroll
         for (int j = 0; j < BPL; ++j) {
-            const u32 b = (tw * BPL + j) * 32 + lane;
-            const bool ok = (valid >> j) & 1u;
+            const u32 grp = tw * BPL + j, b = grp * 32 + lane;
+            const bool ok = (tvalid >> grp) & 1u;
             const bool touch = s_boxdist<DIM>(r, blo[j], bhi[j]) < bmax[j];     // can lower something in the bucket
             const bool hitmax = !(sqdist<DIM>(bmc[j], r) > bmax[j]);            // lowers the bucket's max point
             const bool want = ok && (touch || hitmax);
@@ -183,7 +201,18 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
             }
             const bool flush = want && (hitmax || np[j] >= R);
             const u32 m = __ballot_sync(FULL, flush);
-            if (lane == 0) sts32(fmask + (tw * BPL + j) * 4, m);
+            if (flush) {   // into the group's compacted list; the bucket's lines start moving from HBM to L2 right away
+                sts32(flist + (grp * 32 + __popc(m & ((1u << lane) - 1u))) * 4, b);
+                if (a.prefetch) {
+                    const uint4 br = lds128u(brec + b * 16);
+                    const u32 p0 = br.x & ~3u, bytes = (((br.y + 3u) & ~3u) - p0) * 4u;
+                    l2_prefetch_bulk(dis + p0, bytes);
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c)
+                        if (c < (int)dim) l2_prefetch_bulk(q + (size_t)c * npad + p0, bytes);
+                }
+            }
+            if (lane == 0) sts32(fmask + grp * 4, m);
             if (a.count) {
                 const u32 ne = __popc(__ballot_sync(FULL, flush && !hitmax));
                 if (lane == 0 && ne) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 24)), (u64)ne);
@@ -192,23 +221,27 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         team_sync<WPC>(team);
 
         // ---- 2. bucket passes: every flushed bucket, this warp's run of chunks, all pending samples applied -----------------
-        u32 mw[NW];
+        u32 pre[NW];   // flushed buckets up to and including group w
+        {
+            u32 acc = 0;
 #pragma unroll
-        for (u32 w = 0; w < NW; ++w) mw[w] = lds32(fmask + w * 4);
-        for (;;) {   // batches of at most S_MAXF buckets between two exchanges
-            u32 nf = 0, myb = S_NONE;                 // lane fi remembers the bucket of flush slot fi
+            for (u32 w = 0; w < NW; ++w) {
+                acc += __popc(lds32(fmask + w * 4));
+                pre[w] = acc;
+            }
+        }
+        const u32 total = pre[NW - 1];
+        for (u32 f0 = 0; f0 < total; f0 += S_MAXF) {   // batches of at most S_MAXF buckets between two exchanges
+            const u32 nf = min(total - f0, S_MAXF);
+            u32 myb = S_NONE;                         // lane fi remembers the bucket of flush slot fi
             const u32 pbuf = part + bp * (S_MAXF * WPC * S_REC);
-            while (nf < S_MAXF) {
-                u32 b = S_NONE;
+            for (u32 fi = 0; fi < nf; ++fi) {
+                const u32 f = f0 + fi;
+                u32 w = 0, base = 0;                   // group of the f-th flushed bucket, flushed buckets before that group
 #pragma unroll
-                for (u32 w = 0; w < NW; ++w) {
-                    if (b == S_NONE && mw[w]) {
-                        b = w * 32 + (__ffs(mw[w]) - 1);
-                        mw[w] &= mw[w] - 1;
-                    }
-                }
-                if (b == S_NONE) break;
-                const u32 fi = nf++;
+                for (u32 x = 0; x + 1 < NW; ++x)
+                    if (f >= pre[x]) w = x + 1, base = pre[x];
+                const u32 b = lds32(flist + (w * 32 + (f - base)) * 4);
                 if (lane == fi) myb = b;
                 const uint4 br = lds128u(brec + b * 16);
                 const u32 lo = br.x, hi = br.y, nref = br.z;
@@ -227,12 +260,13 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 for (int c = 0; c < DIM; ++c) bc[c] = 0.0f;
                 for (u32 cb = my0; cb < my1; cb += G) {   // one block: G chunks of 128 positions, 4 per lane each
                     float4 x[DIM][G], old[G];
-                    bool inside[G];
+                    bool inside[G], edge = false;
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const u32 p4 = (cb + g) * 128 + lane * 4;
                         const bool any = cb + g < my1 && p4 < hi && p4 + 3 >= lo;
                         inside[g] = cb + g < my1 && p4 >= lo && p4 + 3 < hi;
+                        edge = edge || (any && !inside[g]);
                         old[g] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);   // never a maximum, never stored
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) x[c][g] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -241,12 +275,16 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
 #pragma unroll
                             for (int c = 0; c < DIM; ++c)
                                 if (c < (int)dim) x[c][g] = ldg128(q + (size_t)c * npad + p4);
-                            if (!inside[g]) {   // a run's first / last group: positions of the neighbour buckets drop out
-                                if (p4 + 0 < lo || p4 + 0 >= hi) old[g].x = -1.0f;
-                                if (p4 + 1 < lo || p4 + 1 >= hi) old[g].y = -1.0f;
-                                if (p4 + 2 < lo || p4 + 2 >= hi) old[g].z = -1.0f;
-                                if (p4 + 3 < lo || p4 + 3 >= hi) old[g].w = -1.0f;
-                            }
+                        }
+                    }
+                    if (__any_sync(FULL, edge)) {   // a run's first / last group: positions of the neighbour buckets drop out
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            const u32 p4 = (cb + g) * 128 + lane * 4;
+                            if (p4 + 0 < lo || p4 + 0 >= hi) old[g].x = -1.0f;
+                            if (p4 + 1 < lo || p4 + 1 >= hi) old[g].y = -1.0f;
+                            if (p4 + 2 < lo || p4 + 2 >= hi) old[g].z = -1.0f;
+                            if (p4 + 3 < lo || p4 + 3 >= hi) old[g].w = -1.0f;
                         }
                     }
                     float4 v[G];
@@ -257,14 +295,14 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     float4 n0 = s_lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if constexpr (DIM > 4) n1 = s_lds128(e0 + 16u);
                     for (u32 i = 0; i < nref; ++i) {
-                        const float4 f0 = n0, f1 = n1;
+                        const float4 f0v = n0, f1v = n1;
                         const u32 en = e0 + min(i + 1, nref - 1) * estep;
                         n0 = s_lds128(en);
                         if constexpr (DIM > 4) n1 = s_lds128(en + 16u);
-                        const float w[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                        const float w8[8] = {f0v.x, f0v.y, f0v.z, f0v.w, f1v.x, f1v.y, f1v.z, f1v.w};
                         u64 RC[DIM];   // the sample in both halves of a packed operand (FADD2 / FFMA2: two positions per instruction)
 #pragma unroll
-                        for (int c = 0; c < DIM; ++c) RC[c] = pk2(w[c], w[c]);
+                        for (int c = 0; c < DIM; ++c) RC[c] = pk2(w8[c], w8[c]);
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
                             u64 PA[DIM], PB[DIM];
@@ -313,85 +351,74 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 const u32 qpos = __reduce_min_sync(FULL, (__float_as_uint(pv) == m) ? bi : S_NONE);
                 const u32 rec = pbuf + (fi * WPC + tw) * S_REC;
                 if (qpos == S_NONE) {
-                    if (lane == 0) sts32(rec, 0u), sts32(rec + 4, S_NONE);
+                    if (lane == 0) sts128u(rec, 0u, S_NONE, 0u, 0u);
                 } else if (bi == qpos) {   // positions are unique: exactly one lane
-                    sts32(rec, m);
-                    sts32(rec + 4, qpos);
-#pragma unroll
-                    for (int c = 0; c < DIM; ++c) sts32(rec + 8 + c * 4, __float_as_uint(bc[c]));
+                    sts128u(rec, m, qpos, 0u, 0u);
+                    s_sts128(rec + 16, bc[0], DIM > 1 ? bc[DIM > 1 ? 1 : 0] : 0.f, DIM > 2 ? bc[DIM > 2 ? 2 : 0] : 0.f, DIM > 3 ? bc[DIM > 3 ? 3 : 0] : 0.f);
+                    if constexpr (DIM > 4)
+                        s_sts128(rec + 32, bc[4], DIM > 5 ? bc[DIM > 5 ? 5 : 0] : 0.f, DIM > 6 ? bc[DIM > 6 ? 6 : 0] : 0.f, DIM > 7 ? bc[DIM > 7 ? 7 : 0] : 0.f);
                 }
             }
-            if (nf == 0) break;
             team_sync<WPC>(team);
-            // ---- owners take the bucket's new maximum: largest value, lowest position over the warps' partials ----------------
+            // ---- every warp merges the partial maxima into its own table: largest value, lowest position ------------------------
             for (u32 fi = 0; fi < nf; ++fi) {
                 const u32 b = __shfl_sync(FULL, myb, fi);
-                if ((b >> 5) / BPL == tw && (b & 31u) == lane) {
-                    u32 m = 0, qpos = S_NONE, src = pbuf + (fi * WPC) * S_REC;
+                u32 m = 0, qpos = S_NONE, src = pbuf + (fi * WPC) * S_REC;
 #pragma unroll
-                    for (int w = 0; w < WPC; ++w) {
-                        const u32 rec = pbuf + (fi * WPC + w) * S_REC;
-                        const u32 mm = lds32(rec), qq = lds32(rec + 4);
-                        if (qq != S_NONE && (qpos == S_NONE || mm > m || (mm == m && qq < qpos))) m = mm, qpos = qq, src = rec;
+                for (int w = 0; w < WPC; ++w) {
+                    const u32 rec = pbuf + (fi * WPC + w) * S_REC;
+                    const uint4 pr = lds128u(rec);
+                    if (pr.y != S_NONE && (qpos == S_NONE || pr.x > m || (pr.x == m && pr.y < qpos))) m = pr.x, qpos = pr.y, src = rec;
+                }
+                if ((b & 31u) == lane) {
+#pragma unroll
+                    for (u32 s = 0; s < NW; ++s)
+                        if ((b >> 5) == s) tmax[s] = __uint_as_float(m), tpos[s] = qpos;
+                    const float4 c0v = s_lds128(src + 16);
+                    float4 c1v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if constexpr (DIM > 4) c1v = s_lds128(src + 32);
+                    // the max point's coordinates, for whoever wins the arg-max (every warp writes the same bits)
+                    s_sts128(bmcs + b * PRB, c0v.x, c0v.y, c0v.z, c0v.w);
+                    if constexpr (DIM > 4) s_sts128(bmcs + b * PRB + 16, c1v.x, c1v.y, c1v.z, c1v.w);
+                    if ((b >> 5) / BPL == tw) {   // the owner: its tests compare against the new maximum, its list is empty again
+                        const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+#pragma unroll
+                        for (int j = 0; j < BPL; ++j)
+                            if (((b >> 5) % BPL) == (u32)j) {
+                                bmax[j] = __uint_as_float(m);
+                                np[j] = 0;
+#pragma unroll
+                                for (int c = 0; c < DIM; ++c) bmc[j][c] = cc[c];
+                            }
+                        sts32(brec + b * 16 + 8, 0u);
                     }
-#pragma unroll
-                    for (int j = 0; j < BPL; ++j)
-                        if (((b >> 5) % BPL) == (u32)j) {
-                            bmax[j] = __uint_as_float(m);
-                            bpos[j] = qpos;
-                            np[j] = 0;
-#pragma unroll
-                            for (int c = 0; c < DIM; ++c) bmc[j][c] = __uint_as_float(lds32(src + 8 + c * 4));
-                        }
-                    sts32(brec + b * 16 + 8, 0u);
                 }
             }
             bp ^= 1u;
-            if (nf < S_MAXF) break;   // the masks are empty
         }
 
-        // ---- 3. arg-max over buckets: largest max, lowest position (KDLineTree.h:56-67) ----------------------------------
-        u32 kmax = 0, cand = S_NONE;
-        int jbest = 0;
+        // ---- 3. arg-max over all buckets, by every warp for itself: largest max, lowest position (KDLineTree.h:56-67) ---------
+        u32 kmax = 0, cand = S_NONE, sb = 0;
 #pragma unroll
-        for (int j = 0; j < BPL; ++j) {
-            if ((valid >> j) & 1u) {
-                const u32 kb = __float_as_uint(bmax[j]);
-                if (cand == S_NONE || kb > kmax || (kb == kmax && bpos[j] < cand)) {
-                    kmax = kb;
-                    cand = bpos[j];
-                    jbest = j;
-                }
+        for (u32 s = 0; s < NW; ++s) {
+            if ((tvalid >> s) & 1u) {
+                const u32 kb = __float_as_uint(tmax[s]);
+                if (cand == S_NONE || kb > kmax || (kb == kmax && tpos[s] < cand)) kmax = kb, cand = tpos[s], sb = s;
             }
         }
         const u32 M = __reduce_max_sync(FULL, kmax);
         const u32 mine = (cand != S_NONE && kmax == M) ? cand : S_NONE;
-        const u32 wpos = __reduce_min_sync(FULL, mine);
-        if (wpos == S_NONE) {
-            if (lane == 0) sts32(amax + tw * S_REC, 0u), sts32(amax + tw * S_REC + 4, S_NONE);
-        } else if (mine == wpos) {   // positions are unique: exactly one lane
-            const u32 rec = amax + tw * S_REC;
-            sts32(rec, M);
-            sts32(rec + 4, wpos);
-#pragma unroll
-            for (int j = 0; j < BPL; ++j)
-                if (j == jbest) {
-#pragma unroll
-                    for (int c = 0; c < DIM; ++c) sts32(rec + 8 + c * 4, __float_as_uint(bmc[j][c]));
-                }
-        }
-        team_sync<WPC>(team);
+        cur = __reduce_min_sync(FULL, mine);
+        const u32 srcl = __ffs(__ballot_sync(FULL, mine == cur)) - 1;   // positions are unique: exactly one lane
+        const u32 bw = __shfl_sync(FULL, sb * 32 + lane, srcl);
+        __syncwarp();   // this warp's own copy of the winner's coordinates (written by another lane, above)
         {
-            u32 m = 0, pos = S_NONE, src = amax;
+            const float4 c0v = s_lds128(bmcs + bw * PRB);
+            float4 c1v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if constexpr (DIM > 4) c1v = s_lds128(bmcs + bw * PRB + 16);
+            const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
 #pragma unroll
-            for (int w = 0; w < WPC; ++w) {
-                const u32 rec = amax + w * S_REC;
-                const u32 mm = lds32(rec), qq = lds32(rec + 4);
-                if (qq != S_NONE && (pos == S_NONE || mm > m || (mm == m && qq < pos))) m = mm, pos = qq, src = rec;
-            }
-            cur = pos;
-#pragma unroll
-            for (int c = 0; c < DIM; ++c) r[c] = __uint_as_float(lds32(src + 8 + c * 4));
+            for (int c = 0; c < DIM; ++c) r[c] = cc[c];
         }
         // ---- output: positions are turned into original ids 32 picks at a time (wrapper.hpp:57-59) -----------------
         if (tw == 0) {
@@ -451,8 +478,8 @@ static int stream_dim(int dim) { return dim <= 3 ? 3 : dim == 4 ? 4 : dim <= 6 ?
 static size_t stream_team_bytes(int dimp, u32 wpc, u32 bpl, u32 R) {
     const size_t SP = 32u * wpc * bpl, PRB = (size_t)((dimp + 3) / 4) * 16, NW = wpc * bpl;
     size_t b = R * SP * PRB;
-    b += SP * 16 + ((NW + 3) & ~(size_t)3) * 4;
-    b += 2 * S_MAXF * wpc * S_REC + wpc * S_REC;
+    b += SP * 16 + SP * PRB + ((NW + 3) & ~(size_t)3) * 4 + SP * 4;
+    b += 2 * S_MAXF * wpc * S_REC;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -462,17 +489,23 @@ bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, Str
     const u32 S = 1u << h;
     const int dimp = stream_dim((int)dim);
     const size_t cap = 227 * 1024 - 256;
-    // warps per cloud: 4 (measured, 100 k-point clouds x 3, 2^7 buckets: a 512-cloud shard samples in 31.8 ms with 4 warps per
-    // cloud, 56 ms with 2, 94 ms with 1; 4096 clouds take 218 - 231 ms whichever way the 16 warps of an SM are grouped -- the
-    // pick is a dependent chain, an SM only overlaps as many of them as it has teams); 1 and 2 stay available as a knob
-    u32 wpc = 4;
+    // warps per cloud (measured, 100 k-point clouds x 3, 2^7 buckets, one B200): a pick is a dependent chain and an SM only
+    // overlaps as many chains as it has teams, so big batches want many small teams and small shards want the chain itself
+    // short.  Sampling ms for 1 / 2 / 4 warps per cloud: 4096 clouds 197 / 203 / 214, 2048: 101 / 104 / 117, 1024: 85 / 54 / 60,
+    // 512: 94 / 56 / 31.  Records of more than 4 dimensions need the shared memory of a 4-warp team for useful pending lists.
+    const size_t slots = (size_t)(S_THREADS / 32) * n_sms;   // one-warp teams the GPU holds (2368)
+    u32 wpc = dimp > 4 ? 4 : (B >= slots * 27 / 32 ? 1 : (B >= slots / 3 ? 2 : 4));
     if (tu.stream_warps == 1 || tu.stream_warps == 2 || tu.stream_warps == 4) wpc = (u32)tu.stream_warps;
     if (S > 128) wpc = 4;
-    const u32 bpl = wpc == 1 ? 4 : wpc == 2 ? 2 : (S <= 128 ? 1 : S <= 256 ? 2 : 4);
-    const u32 teams = S_THREADS / 32 / wpc;
-    u32 R = S_MAXR;
-    while (R > 2 && teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) --R;
-    if (teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) return false;
+    u32 bpl = 0, teams = 0, R = 0;
+    for (;; wpc *= 2) {   // a team too small for its shared memory (wide records): the next size up
+        bpl = wpc == 1 ? 4 : wpc == 2 ? 2 : (S <= 128 ? 1 : S <= 256 ? 2 : 4);
+        teams = S_THREADS / 32 / wpc;
+        R = S_MAXR;
+        while (R > 3 && teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) --R;
+        if (teams * stream_team_bytes(dimp, wpc, bpl, R) <= cap) break;
+        if (wpc == 4) return false;
+    }
     pl->dimp = dimp;
     pl->wpc = wpc;
     pl->bpl = bpl;
@@ -521,6 +554,7 @@ cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, si
     a.R = pl.rs;
     a.team_bytes = pl.team_bytes;
     a.count = count ? 1u : 0u;
+    a.prefetch = tuning().prefetch != 0 ? 1u : 0u;
     a.negzero = 0x8000000080000000ull;
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;

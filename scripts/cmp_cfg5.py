@@ -12,6 +12,7 @@ n, d, k, h = 100000, int(args[0]) if args else 3, 8192, 7
 Bs = [int(x) for x in args[1:]] or [512]
 wpcs = [int(x) for x in opt.get("wpc", "-1").split(",")]
 ncheck = int(opt.get("check", "2"))
+if "prefetch" in opt: capi.set_tuning("PREFETCH", int(opt["prefetch"]))
 nreal = 32
 base = np.stack([synth.uniform(3000 + b, n, d) for b in range(nreal)])
 want = {b: O.kdline(base[b], k, h, 0) for b in range(ncheck)}

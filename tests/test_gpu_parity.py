@@ -532,13 +532,13 @@ def test_cfg5_batch_100k_to_8192(d, oracle, golden):
 @pytest.mark.parametrize("d,B,ncheck", [(3, 1200, 12), (6, 320, 4)])
 def test_cfg5_production_plan(d, B, ncheck, oracle):
     """BASELINE.json configs[4] on the plan the full 4096-cloud batch (and every shard of it down to one eighth) takes:
-    the grid-wide build + the streaming sampler with 4 warps per cloud, 16 warps per SM.  A seeded subset of the clouds is
-    checked against the oracle, every cloud for the properties an exact FPS result has."""
+    the grid-wide build + the streaming sampler (teams of 1 / 2 / 4 warps per cloud by batch size, 16 warps per SM).  A
+    seeded subset of the clouds is checked against the oracle, every cloud for the properties an exact FPS result has."""
     n, k, h = 100000, 8192, 7
     pcs = synth.uniform_batch(3000, B, n, d)
     got = capi.kdline_batch(pcs, k, h, devices=[0])
     plan = capi.last_plan()
-    assert "kdline_stream_kernel" in plan and "WPC=4" in plan and "gb_* grid-wide build" in plan, plan
+    assert "kdline_stream_kernel" in plan and ("WPC=2" if d == 3 else "WPC=4") in plan and "gb_* grid-wide build" in plan, plan
     for b in range(B):
         assert got[b].max() < n
     for b in range(0, B, 7):
@@ -546,11 +546,16 @@ def test_cfg5_production_plan(d, B, ncheck, oracle):
     rng = np.random.default_rng(d)
     for b in sorted({0, B - 1} | set(int(x) for x in rng.integers(0, B, ncheck - 2))):
         np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, 0), err_msg=f"cloud {b}: {plan}")
-    # the shard one of eight GPUs gets takes the same kernel
+    # the shard one of eight GPUs gets takes the same kernel with 4 warps per cloud; the full batch's one-warp teams are
+    # forced onto a slice of it (the planner picks them from ~2000 clouds per GPU on)
     if d == 3:
         shard = capi.kdline_batch(pcs[:512], k, h, devices=[0])
         assert "kdline_stream_kernel" in capi.last_plan() and "WPC=4" in capi.last_plan(), capi.last_plan()
         np.testing.assert_array_equal(shard, got[:512])
+        with capi.tuning(stream_warps=1):
+            one = capi.kdline_batch(pcs[:400], k, h, devices=[0])
+            assert "WPC=1" in capi.last_plan(), capi.last_plan()
+        np.testing.assert_array_equal(one, got[:400])
 
 
 def test_executed_work_counters_of_the_streaming_sampler(oracle):
