@@ -513,8 +513,8 @@ def cfg5(wl, D, steps=2):
     if D.rank != 0:
         return None
     hbm_gbs, sm_mhz, how = peaks()
-    pts, pu, passes, early, tests, picks, clouds = [int(x) for x in cnt[:7]]
-    byts = pts * 4 * (d + 2)                                   # executed bytes: D coordinates + distance read, distance written at most
+    pts, pu, passes, early, tests, picks, clouds, stored = [int(x) for x in cnt[:8]]
+    byts = pts * 4 * (d + 1) + stored * 4                      # executed bytes: D coordinates + distance read per point, 4 per distance written back
     traffic = None
     tj = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tj):
@@ -533,12 +533,14 @@ def cfg5(wl, D, steps=2):
                          "frac": byts / (sample_ms * 1e-3) / 1e9 / hbm_gbs, "traffic": traffic, "kernel": "kdline_stream_kernel",
                          "kernel_ms": sample_ms,
                          "executed_per_pick": {"points_scanned": pts / max(picks, 1), "point_updates": pu / max(picks, 1),
+                                               "distances_stored": stored / max(picks, 1),
                                                "bucket_passes": passes / max(picks, 1), "early_passes": early / max(picks, 1),
                                                "bucket_tests": tests / max(picks, 1)},
                          "fp32_frac": (pu * (3 * d + 1) + tests * 8 * d) / (sample_ms * 1e-3) / 1e12 / fp32_peak,
                          "note": f"W_exec from the kernel's own counters on this rank's shard (SURVEY.md 8(d)): every point of a bucket pass "
-                                 f"moves at most 4(D+2) = {4 * (d + 2)} bytes (D coordinates + distance read, distance written back only if it "
-                                 f"changed), so this is an upper bound of the DRAM traffic (`traffic` = ncu dram bytes of the same launch); peak {how}"},
+                                 f"reads 4(D+1) = {4 * (d + 1)} bytes (D coordinates + its distance) and a distance is written back only if it "
+                                 f"changed (counted); the reference algorithm's 4(D+2) per point-update would be {pu * 4 * (d + 2) / 1e9:.0f} GB. "
+                                 f"`traffic` = ncu dram bytes of the same launch shape (profiles/traffic.json); peak {how}"},
             "plan": plan, "gpu_launches": int(launches), "parity_checked_clouds": checked}
 
 

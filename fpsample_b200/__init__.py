@@ -7,7 +7,9 @@ Same Python surface as the reference front-end (src/fpsample/__init__.py:35-65, 
     bucket_fps_kdtree_sampling(pc, n_samples, start_idx=None)        -> uint64[n_samples]   (:145-171)
     fps_npdu_sampling(pc, n_samples, w=None, start_idx=None)         -> uint64[n_samples]   (:66-103)
 
-(fps_npdu_kdtree_sampling, which needs nanoflann's kNN, is the one entry that raises NotImplementedError) plus batched twins over [B, N, D] arrays (new):
+    fps_npdu_kdtree_sampling(pc, n_samples, w=None, start_idx=None)  -> uint64[n_samples]   (:106-142)
+
+plus batched twins over [B, N, D] arrays (new):
 
     fps_sampling_batch(pcs, n_samples, start_idx=None, devices=None)               -> uint64[B, n_samples]
     bucket_fps_kdline_sampling_batch(pcs, n_samples, h, start_idx=None, devices=None)
@@ -33,6 +35,7 @@ try:
         _bucket_fps_kdtree_sampling_batch,
         _batch_ptr,
         _device_count,
+        _fps_npdu_kdtree_sampling,
         _fps_npdu_sampling,
         _fps_sampling,
         _fps_sampling_batch,
@@ -268,14 +271,6 @@ def bucket_fps_kdtree_sampling_batch(pcs: np.ndarray, n_samples: int,
                                              None if devices is None else list(devices))
 
 
-def _out_of_scope(name):
-    def f(*a, **k):
-        raise NotImplementedError(
-            f"{name} is outside the accelerated hot path of fpsample_b200 (see DESIGN.md, 'out of scope')")
-    f.__name__ = name
-    return f
-
-
 def fps_npdu_sampling(pc: np.ndarray, n_samples: int, w: Optional[int] = None,
                       start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
     """FPS with the nearest-point-distance-updating heuristic over an index window (reference:
@@ -299,9 +294,33 @@ def fps_npdu_sampling(pc: np.ndarray, n_samples: int, w: Optional[int] = None,
     return _fps_npdu_sampling(pc, n_samples, w, start_idx)
 
 
-fps_npdu_kdtree_sampling = _out_of_scope("fps_npdu_kdtree_sampling")
+def fps_npdu_kdtree_sampling(pc: np.ndarray, n_samples: int, w: Optional[int] = None,
+                             start_idx: Optional[Union[int, List[int]]] = None) -> np.ndarray:
+    """FPS with the NPDU heuristic over the w NEAREST points of every pick instead of an index window (reference:
+    src/fpsample/__init__.py:106-142 -> src/lib.cpp:369-465).  NOT exact FPS; needs no dimensional locality.
+
+    w: number of neighbours updated per pick, default n_pts / n_samples * 16 (capped to n_pts with the reference's warning).
+    The reference finds the neighbours with nanoflann; here the GPU selects them by brute force, which gives the same set --
+    and the same indices -- unless several points share the w-th nearest distance exactly (see include/fps_b200.h).
+    """
+    assert n_samples >= 1, "n_samples should be >= 1"
+    assert pc.ndim == 2
+    n_pts, _ = pc.shape
+    assert n_pts >= n_samples, "n_pts should be >= n_samples"
+    assert start_idx is None or 0 <= start_idx < n_pts, "start_idx should be None or 0 <= start_idx < n_pts"
+    if isinstance(start_idx, list):
+        assert len(start_idx) <= n_samples, "len(start_idx) should be <= n_samples"
+    pc = np.ascontiguousarray(pc, dtype=np.float32)
+    w = w or int(n_pts / n_samples * 16)
+    if w >= n_pts:
+        warnings.warn(f"k is too large, set to {n_pts}")
+        w = n_pts
+    start_idx = get_start_idx(n_pts, start_idx)
+    return _fps_npdu_kdtree_sampling(pc, n_samples, w, start_idx)
+
 
 __all__ = [
+    "__doc__",
     "__version__",
     "fps_sampling",
     "bucket_fps_kdline_sampling",

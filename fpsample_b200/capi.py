@@ -28,6 +28,8 @@ EXPORTS = {
     "fps_b200_kdline_build_dev": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p] * 4 + [ctypes.c_size_t, ctypes.c_void_p]),
     "fps_b200_npdu": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p]),
     "fps_b200_npdu_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
+    "fps_b200_npdu_kdtree": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p]),
+    "fps_b200_npdu_kdtree_batch": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 5 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "fps_b200_seqsum_dev": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "fps_b200_device_count": (ctypes.c_int, []),
     "fps_b200_version": (ctypes.c_char_p, []),
@@ -191,6 +193,25 @@ def npdu(pc, k, w, start=0):
     pc = _f32(pc, 2)
     out = np.empty(k, dtype=np.uint64)
     _check("fps_b200_npdu", lib().fps_b200_npdu(pc.ctypes.data, pc.shape[0], pc.shape[1], k, w, start, out.ctypes.data))
+    return out
+
+
+def npdu_kdtree(pc, k, w, start=0):
+    pc = _f32(pc, 2)
+    out = np.empty(k, dtype=np.uint64)
+    _check("fps_b200_npdu_kdtree", lib().fps_b200_npdu_kdtree(pc.ctypes.data, pc.shape[0], pc.shape[1], k, w, start, out.ctypes.data))
+    return out
+
+
+def npdu_kdtree_batch(pcs, k, w, start=None, devices=None):
+    pcs = _f32(pcs, 3)
+    b, n, d = pcs.shape
+    st = _starts(start, b)
+    dv = None if devices is None else np.asarray(devices, dtype=np.int32)
+    out = np.empty((b, k), dtype=np.uint64)
+    _check("fps_b200_npdu_kdtree_batch", lib().fps_b200_npdu_kdtree_batch(
+        pcs.ctypes.data, b, n, d, k, w, None if st is None else st.ctypes.data, out.ctypes.data,
+        None if dv is None else dv.ctypes.data, 0 if dv is None else dv.size))
     return out
 
 

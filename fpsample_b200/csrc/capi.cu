@@ -734,6 +734,8 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
         size_t ws_need;
         if (j.algo == FPS_ALGO_NPDU) {
             ws_need = npdu_workspace_bytes(nb, j.n);
+        } else if (j.algo == FPS_ALGO_NPDU_KNN) {
+            ws_need = npdu_knn_workspace_bytes(nb, j.n);
         } else if (j.algo == FPS_ALGO_VANILLA) {
             WsLayout L;
             vanilla_layout(nb, j.n, j.dim, cx->n_sms, &L);
@@ -758,9 +760,10 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
                                cudaMemcpyHostToDevice, ln.st));
         }
         if (!dev_in) CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
-        if (j.algo == FPS_ALGO_NPDU) {
-            cudaError_t e = launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, d_res, ln.ws.p,
-                                        cx->n_sms, ln.st);
+        if (j.algo == FPS_ALGO_NPDU || j.algo == FPS_ALGO_NPDU_KNN) {
+            cudaError_t e = j.algo == FPS_ALGO_NPDU
+                                ? launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, d_res, ln.ws.p, cx->n_sms, ln.st)
+                                : launch_npdu_knn(d_in, nb, j.n, j.dim, j.k, j.h /* neighbours */, d_starts, d_res, ln.ws.p, cx->n_sms, ln.st);
             if (e == cudaErrorNotSupported) {
                 cudaGetLastError();
                 set_err("fps_npdu: dim > 64 or more than 6.5 M points are not supported");
@@ -769,7 +772,10 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
                 set_err("npdu launch failed: %s", cudaGetErrorString(e));
                 rc = FPS_ERR_CUDA + (int)e;
             } else {
-                set_plan("npdu_kernel clouds=%zu (one CTA per cloud, 256-point segment maxima in shared memory) window=%zu", nb, j.h);
+                if (j.algo == FPS_ALGO_NPDU)
+                    set_plan("npdu_kernel clouds=%zu (one CTA per cloud, 256-point segment maxima in shared memory) window=%zu", nb, j.h);
+                else
+                    set_plan("npdu_knn_kernel clouds=%zu (one CTA per cloud, radix select of the k-th nearest distance) neighbours=%zu", nb, j.h);
             }
         } else if (j.algo == FPS_ALGO_VANILLA)
             rc = enqueue_vanilla(d_in, nb, j.n, j.dim, j.k, d_starts, j.n_starts, d_res, ln.ws.p, ln.ws.cap, cx->n_sms, ln.st);
@@ -1160,6 +1166,31 @@ int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_samples, s
     }
     ShardJob j{FPS_ALGO_NPDU, points, 1, n, dim, n_samples, window, &start_idx, 1, out};
     return run_batch(j, nullptr, 1);
+}
+
+int fps_b200_npdu_kdtree(const float *points, size_t n, size_t dim, size_t n_samples, size_t k, size_t start_idx, size_t *out) {
+    int rc = check_common(points, 1, n, dim, n_samples, out);
+    if (rc) return rc;
+    if (start_idx >= n) {
+        set_err("start_idx %zu out of range (n=%zu)", start_idx, n);
+        return FPS_ERR_START;
+    }
+    ShardJob j{FPS_ALGO_NPDU_KNN, points, 1, n, dim, n_samples, k, &start_idx, 1, out};
+    return run_batch(j, nullptr, 1);
+}
+
+int fps_b200_npdu_kdtree_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t k,
+                               const size_t *start, size_t *out, const int *devices, int n_devices) {
+    int rc = check_common(points, B, n, dim, n_samples, out);
+    if (rc) return rc;
+    if (start)
+        for (size_t b = 0; b < B; ++b)
+            if (start[b] >= n) {
+                set_err("start[%zu]=%zu out of range (n=%zu)", b, start[b], n);
+                return FPS_ERR_START;
+            }
+    ShardJob j{FPS_ALGO_NPDU_KNN, points, B, n, dim, n_samples, k, start, 1, out};
+    return run_batch(j, devices, n_devices);
 }
 
 int fps_b200_npdu_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t window,

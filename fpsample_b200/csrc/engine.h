@@ -123,7 +123,7 @@ struct StreamPlan {
 bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl);
 cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                  u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, bool count, cudaStream_t st);
-cudaError_t stream_debug_counters(u64 *out16);   // points scanned, point-updates, flushes, early flushes, bucket tests, picks, clouds
+cudaError_t stream_debug_counters(u64 *out16);   // points scanned, point-updates, passes, early passes, bucket tests, picks, clouds, distances stored
 
 // ---- kd-line, one huge cloud on the whole GPU: points in shared memory, batched picks per grid-wide exchange (kdline_grid.cu) --
 struct GridPlan {
@@ -156,6 +156,11 @@ cudaError_t launch_kdtree_map(u64 *out, const unsigned char *region, size_t regi
 size_t npdu_workspace_bytes(size_t B, size_t n);
 cudaError_t launch_npdu(const float *pts, size_t B, size_t n, size_t dim, size_t k, size_t w, const u64 *starts, u64 *out,
                         void *ws, int n_sms, cudaStream_t st);
+
+// ---- fps_npdu_kdtree_sampling: k-nearest-neighbour update, one CTA per cloud, radix select of the k-th distance (npdu.cu) ------
+size_t npdu_knn_workspace_bytes(size_t B, size_t n);
+cudaError_t launch_npdu_knn(const float *pts, size_t B, size_t n, size_t dim, size_t k, size_t w, const u64 *starts, u64 *out,
+                            void *ws, int n_sms, cudaStream_t st);
 
 // ---- test entry for the tile-parallel sequential sum (seqsum.cu) ------------------------------------------------------
 cudaError_t launch_seqsum(const float *x, size_t n, float *out, u32 *fast_tiles, int epl, cudaStream_t st);

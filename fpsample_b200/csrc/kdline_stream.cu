@@ -139,18 +139,19 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     }
 
     // ---- the buckets this lane OWNS (tests, pending list): warp tw, slot j, lane l own bucket (tw * BPL + j) * 32 + l ------
-    float blo[BPL][DIM], bhi[BPL][DIM], bmc[BPL][DIM], bmax[BPL];
+    float blo[BPL][DIM], bhi[BPL][DIM], bmc[BPL][DIM];
+    float bmax_[WPC == 1 ? 1 : BPL];   // (a one-warp team owns every bucket: its table below IS the owned state)
     u32 np[BPL];
     // ---- every warp's own copy of ALL bucket maxima: lane l, slot s = bucket s * 32 + l ----------------------------------------
     float tmax[NW];
     u32 tpos[NW], tvalid = 0;
+#define S_OWNMAX(j) (*(WPC == 1 ? &tmax[(j)] : &bmax_[WPC == 1 ? 0 : (j)]))
     team_sync<WPC>(team);
     {
         const float *fbox = reinterpret_cast<const float *>(rg) + (size_t)(dim + 2) * npad + a.nlo_pad;
 #pragma unroll
         for (int j = 0; j < BPL; ++j) {
             const u32 b = (tw * BPL + j) * 32 + lane;
-            bmax[j] = FLT_MAX;   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103)
             np[j] = 0;
 #pragma unroll
             for (int c = 0; c < DIM; ++c) blo[j][c] = bhi[j][c] = bmc[j][c] = 0.0f;
@@ -172,6 +173,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
             tpos[s] = S_NONE;
             if (b < S && br.y > br.x) tvalid |= 1u << s;
         }
+#pragma unroll
+        for (int j = 0; j < BPL; ++j) S_OWNMAX(j) = FLT_MAX;   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103)
     }
 
     u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;   // POSITION in the permuted array (wrapper.hpp:54-55)
@@ -188,8 +191,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         for (int j = 0; j < BPL; ++j) {
             const u32 grp = tw * BPL + j, b = grp * 32 + lane;
             const bool ok = (tvalid >> grp) & 1u;
-            const bool touch = s_boxdist<DIM>(r, blo[j], bhi[j]) < bmax[j];     // can lower something in the bucket
-            const bool hitmax = !(sqdist<DIM>(bmc[j], r) > bmax[j]);            // lowers the bucket's max point
+            const bool touch = s_boxdist<DIM>(r, blo[j], bhi[j]) < S_OWNMAX(j);   // can lower something in the bucket
+            const bool hitmax = !(sqdist<DIM>(bmc[j], r) > S_OWNMAX(j));          // lowers the bucket's max point
             const bool want = ok && (touch || hitmax);
             if (want) {   // remember the sample: pend[np][bucket]
                 const u32 e = pend + (np[j] * SP + b) * PRB;
@@ -321,6 +324,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     for (int g = 0; g < G; ++g) {
                         const u32 p4 = (cb + g) * 128 + lane * 4;
                         const bool ch = v[g].x != old[g].x || v[g].y != old[g].y || v[g].z != old[g].z || v[g].w != old[g].w;
+                        if (a.count) {   // distances written back: whole 16-byte groups inside the bucket, single values at its ends
+                            const u32 nst = inside[g] ? (ch ? 4u : 0u)
+                                                      : (u32)(v[g].x != old[g].x) + (u32)(v[g].y != old[g].y) + (u32)(v[g].z != old[g].z) + (u32)(v[g].w != old[g].w);
+                            const u32 tot = __reduce_add_sync(FULL, nst);
+                            if (lane == 0 && tot) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 56)), (u64)tot);
+                        }
                         if (ch) {
                             if (inside[g]) {
                                 __stcg(reinterpret_cast<float4 *>(dis + p4), v[g]);
@@ -370,28 +379,33 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     const uint4 pr = lds128u(rec);
                     if (pr.y != S_NONE && (qpos == S_NONE || pr.x > m || (pr.x == m && pr.y < qpos))) m = pr.x, qpos = pr.y, src = rec;
                 }
-                if ((b & 31u) == lane) {
+                // (written as selects on purpose: an unrolled `if (slot == s) table[s] = ...` is turned into a dynamically indexed
+                // store by the compiler, which moves the whole table to local memory)
+                const bool mineb = (b & 31u) == lane;
 #pragma unroll
-                    for (u32 s = 0; s < NW; ++s)
-                        if ((b >> 5) == s) tmax[s] = __uint_as_float(m), tpos[s] = qpos;
+                for (u32 s = 0; s < NW; ++s) {
+                    const bool hit = mineb && (b >> 5) == s;
+                    tmax[s] = hit ? __uint_as_float(m) : tmax[s];
+                    tpos[s] = hit ? qpos : tpos[s];
+                }
+                if (mineb) {
                     const float4 c0v = s_lds128(src + 16);
                     float4 c1v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if constexpr (DIM > 4) c1v = s_lds128(src + 32);
                     // the max point's coordinates, for whoever wins the arg-max (every warp writes the same bits)
                     s_sts128(bmcs + b * PRB, c0v.x, c0v.y, c0v.z, c0v.w);
                     if constexpr (DIM > 4) s_sts128(bmcs + b * PRB + 16, c1v.x, c1v.y, c1v.z, c1v.w);
-                    if ((b >> 5) / BPL == tw) {   // the owner: its tests compare against the new maximum, its list is empty again
-                        const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                    const bool own = (b >> 5) / BPL == tw;   // the owner: its tests compare against the new maximum, its list is empty again
+                    const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
 #pragma unroll
-                        for (int j = 0; j < BPL; ++j)
-                            if (((b >> 5) % BPL) == (u32)j) {
-                                bmax[j] = __uint_as_float(m);
-                                np[j] = 0;
+                    for (int j = 0; j < BPL; ++j) {
+                        const bool hit = own && ((b >> 5) % BPL) == (u32)j;
+                        if constexpr (WPC != 1) S_OWNMAX(j) = hit ? __uint_as_float(m) : S_OWNMAX(j);
+                        np[j] = hit ? 0u : np[j];
 #pragma unroll
-                                for (int c = 0; c < DIM; ++c) bmc[j][c] = cc[c];
-                            }
-                        sts32(brec + b * 16 + 8, 0u);
+                        for (int c = 0; c < DIM; ++c) bmc[j][c] = hit ? cc[c] : bmc[j][c];
                     }
+                    if (own) sts32(brec + b * 16 + 8, 0u);
                 }
             }
             bp ^= 1u;
@@ -443,6 +457,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         atomicAdd(cs + 6, 1ull);               // clouds
     }
     team_sync<WPC>(team);   // the team's shared memory is reused by its next cloud
+#undef S_OWNMAX
 }
 
 template <int DIM, int WPC, int BPL>
@@ -491,10 +506,12 @@ bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, Str
     const size_t cap = 227 * 1024 - 256;
     // warps per cloud (measured, 100 k-point clouds x 3, 2^7 buckets, one B200): a pick is a dependent chain and an SM only
     // overlaps as many chains as it has teams, so big batches want many small teams and small shards want the chain itself
-    // short.  Sampling ms for 1 / 2 / 4 warps per cloud: 4096 clouds 197 / 203 / 214, 2048: 101 / 104 / 117, 1024: 85 / 54 / 60,
-    // 512: 94 / 56 / 31.  Records of more than 4 dimensions need the shared memory of a 4-warp team for useful pending lists.
+    // short.  Sampling ms for 1 / 2 / 4 warps per cloud: 4096 clouds 171 / 175 / 214, 2048: 86 / 88 / 117, 1024: 85 / 44 / 60,
+    // 512: 94 / 56 / 28.  One-warp teams only have room for 4 pending samples per bucket (0.23 early passes per pick, +18 % DRAM
+    // traffic) and buy nothing over two: they stay a knob.  Records of more than 4 dimensions need the shared memory of a
+    // 4-warp team for useful pending lists.
     const size_t slots = (size_t)(S_THREADS / 32) * n_sms;   // one-warp teams the GPU holds (2368)
-    u32 wpc = dimp > 4 ? 4 : (B >= slots * 27 / 32 ? 1 : (B >= slots / 3 ? 2 : 4));
+    u32 wpc = dimp > 4 ? 4 : (B >= slots / 3 ? 2 : 4);
     if (tu.stream_warps == 1 || tu.stream_warps == 2 || tu.stream_warps == 4) wpc = (u32)tu.stream_warps;
     if (S > 128) wpc = 4;
     u32 bpl = 0, teams = 0, R = 0;

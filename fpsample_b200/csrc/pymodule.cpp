@@ -157,6 +157,40 @@ static py::array_t<size_t> npdu_py(farray points, size_t n_samples, size_t k, py
     return out;
 }
 
+// src/lib.cpp:369-465 (fps_npdu_kdtree_sampling_py) + check_py_input (:52-109)
+static py::array_t<size_t> npdu_kdtree_py(farray points, size_t n_samples, size_t k, py::object start_idx_obj) {
+    size_t start = 0;
+    bool is_array = false;
+    if (py::isinstance<py::int_>(start_idx_obj)) start = start_idx_obj.cast<size_t>();
+    else if (py::isinstance<py::array_t<size_t>>(start_idx_obj)) is_array = true;
+    else throw py::type_error("start_idx must be int or 1D numpy array of size_t");
+    if (points.ndim() != 2)
+        throw py::value_error("points must be a 2D array, but got shape " + std::to_string(points.ndim()));
+    const size_t P = (size_t)points.shape(0), C = (size_t)points.shape(1);
+    if (C == 0) throw py::value_error("points must have at least one column");
+    if (n_samples > P)
+        throw py::value_error("n_samples must be less than the number of points: n_samples=" + std::to_string(n_samples) +
+                              ", P=" + std::to_string(P));
+    if (is_array) {   // the reference validates first and refuses afterwards (src/lib.cpp:385-390)
+        PyErr_SetString(PyExc_NotImplementedError, "Array of start indices not implemented yet");
+        throw py::error_already_set();
+    }
+    if (start >= P)
+        throw py::value_error("start_idx must be less than the number of points: start_idx=" + std::to_string(start) +
+                              ", P=" + std::to_string(P));
+    py::array_t<size_t> out(n_samples);
+    if (n_samples == 0) return out;
+    int rc;
+    {
+        const float *src = points.data();
+        size_t *dst = out.mutable_data();
+        py::gil_scoped_release rel;
+        rc = fps_b200_npdu_kdtree(src, P, C, n_samples, k, start, dst);
+    }
+    if (rc != 0) raise_rc("fps_b200_npdu_kdtree", rc);
+    return out;
+}
+
 // ---- batched entries (new) -----------------------------------------------------------------------------
 // Large index arrays are handed out over page-locked memory from the library (fps_b200_host_alloc): the device-to-host
 // copy then runs at PCIe speed straight into the array the caller gets, with no pageable bounce buffer and no first-touch
@@ -286,6 +320,8 @@ PYBIND11_MODULE(_fpsample, m, py::mod_gil_not_used()) {
           "QuickFPS full kd tree. points: N x C float32 (C <= 8); n_samples; start_idx: int. Returns uint64[n_samples].");
     m.def("_fps_npdu_sampling", &npdu_py,
           "FPS with the NPDU index-window heuristic. points: N x C float32; n_samples; k (window); start_idx: int. Returns uint64[n_samples].");
+    m.def("_fps_npdu_kdtree_sampling", &npdu_kdtree_py,
+          "FPS with the NPDU heuristic over the k nearest points. points: N x C float32; n_samples; k; start_idx: int. Returns uint64[n_samples].");
     m.def("_bucket_fps_kdtree_sampling_batch",
           [](farray p, size_t k, py::object s, py::object d) { return batch_py(FPS_ALGO_KDTREE, p, k, 0, s, d); },
           "Batched QuickFPS full kd tree. points: B x N x C; start_idx: None|int|int[B]; devices: None|list[int].");

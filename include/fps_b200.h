@@ -99,6 +99,17 @@ FPS_API int fps_b200_npdu(const float *points, size_t n, size_t dim, size_t n_sa
 FPS_API int fps_b200_npdu_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t window,
                         const size_t *start, size_t *out_indices, const int *devices, int n_devices);
 
+/* FPS with the nearest-point-distance-updating heuristic over the k NEAREST points (NOT exact FPS).  Replaces
+ * fps_npdu_kdtree_sampling_py (src/lib.cpp:369-465; its neighbour search is nanoflann's, src/nanoflann.hpp): after a full
+ * min-update against the start point, every pick min-updates its k nearest points (binary32 distances in the reference's
+ * arithmetic, lib.cpp:33-41; k capped at n, :407) and the next pick is the arg-max over all points, lowest index among equals
+ * (:438-442).  Same indices as the reference whenever the k-th nearest distance of a pick is not shared by more candidates
+ * than there are places left (exact ties there are taken in index order here, in nanoflann's traversal order there). */
+FPS_API int fps_b200_npdu_kdtree(const float *points, size_t n, size_t dim, size_t n_samples, size_t k, size_t start_idx,
+                         size_t *out_indices);
+FPS_API int fps_b200_npdu_kdtree_batch(const float *points, size_t B, size_t n, size_t dim, size_t n_samples, size_t k,
+                               const size_t *start, size_t *out_indices, const int *devices, int n_devices);
+
 /* ---- multi-GPU: shards on every GPU, indices gathered to rank 0 over NCCL (new) ----------------------
  * Clouds are independent: a batch of n_clouds is cut into contiguous shards (remainder to the low ranks, the rule of the
  * *_batch entries), every GPU samples its shard with NO inter-GPU traffic, and the only exchange is the gather of the index
@@ -129,7 +140,8 @@ FPS_API int fps_b200_gather_indices(const uint64_t *local, size_t nb, size_t k, 
 #define FPS_ALGO_VANILLA 0
 #define FPS_ALGO_KDLINE 1
 #define FPS_ALGO_KDTREE 2
-#define FPS_ALGO_NPDU 3 /* host-pointer entries only */
+#define FPS_ALGO_NPDU 3     /* host-pointer entries only */
+#define FPS_ALGO_NPDU_KNN 4 /* host-pointer entries only */
 
 /* bytes of scratch the *_dev calls need on the current device for this shape (256-byte aligned base) */
 FPS_API size_t fps_b200_workspace_bytes(int algo, size_t B, size_t n, size_t dim, size_t k, size_t height);
@@ -174,7 +186,7 @@ FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kerne
 #define FPS_DBG_BUILD 2
 #define FPS_DBG_GRID 3
 #define FPS_DBG_STREAM 4 /* executed work of the streaming sampler (tuning knob COUNT=1): points scanned, point-updates,
-                          bucket passes, early passes (full pending list), bucket tests, picks, clouds */
+                          bucket passes, early passes (full pending list), bucket tests, picks, clouds, distances written back */
 FPS_API int fps_b200_debug_counters(int which, uint64_t *out16);
 /* Planner overrides (tests, experiments).  The library reads FPS_B200_<NAME> from the environment ONCE, at first use; after
  * that only this call changes a knob.  value -1 = the planner's own choice.  Names: GRID, GROUP, GRIDBUILD, VANILLA_KD, PIPE,

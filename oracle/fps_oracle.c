@@ -111,6 +111,53 @@ int oracle_fps_npdu(const float *pts, size_t n, size_t d, size_t n_samples, size
     return 0;
 }
 
+/*
+ * FPS with the nearest-point-distance-updating heuristic over the k NEAREST points (fps_npdu_kdtree_sampling).
+ * Reference: fps_npdu_kdtree_sampling_py, src/lib.cpp:369-465.  After the full min-update against the start point every
+ * pick min-updates its k_use = min(k, n) nearest points (lib.cpp:407, 421-436; distances as in PointCloud::kdtree_distance,
+ * lib.cpp:33-41) and the next pick is the first maximum over all points (strict '>' from -1, lib.cpp:438-442).  The
+ * reference obtains the neighbours from nanoflann (vendored third party, src/nanoflann.hpp v1.8.0: KDTreeSingleIndexAdaptor,
+ * leaf size 10, KNNResultSet); what it computes only depends on the SET of the k nearest points, which this restatement
+ * finds by brute force.  When more points share the k-th nearest distance than there are places left, the reference keeps
+ * whichever nanoflann's traversal met first; here they are taken in index order (the one documented difference -- the
+ * golden vectors pin the restatement on clouds without such ties).
+ */
+typedef struct { float d; size_t i; } nk_t;
+static int nk_cmp(const void *a, const void *b) {
+    const nk_t *x = (const nk_t *)a, *y = (const nk_t *)b;
+    if (x->d < y->d) return -1;
+    if (x->d > y->d) return 1;
+    return x->i < y->i ? -1 : (x->i > y->i ? 1 : 0);
+}
+int oracle_fps_npdu_kdtree(const float *pts, size_t n, size_t d, size_t n_samples, size_t k, size_t start, size_t *out) {
+    if (n == 0 || d == 0 || n_samples == 0 || n_samples > n) return 3;
+    if (start >= n) return 2;
+    float *dm = (float *)malloc(n * sizeof(float));
+    nk_t *nb = (nk_t *)malloc(n * sizeof(nk_t));
+    if (!dm || !nb) return 3;
+    for (size_t i = 0; i < n; ++i) dm[i] = sqdist(pts + i * d, pts + start * d, d);   /* min(+inf, .), lib.cpp:446-453 */
+    size_t cur = start;
+    out[0] = cur;
+    const size_t k_use = k < n ? k : n;
+    for (size_t t = 1; t < n_samples; ++t) {
+        /* lib.cpp:412-436: the query is the previous pick (for t == 1 that is the start point again) */
+        const float *q = pts + cur * d;
+        for (size_t i = 0; i < n; ++i) { nb[i].d = sqdist(pts + i * d, q, d); nb[i].i = i; }
+        qsort(nb, n, sizeof(nk_t), nk_cmp);
+        for (size_t x = 0; x < k_use; ++x)
+            if (nb[x].d < dm[nb[x].i]) dm[nb[x].i] = nb[x].d;
+        float best = -1.0f;
+        size_t bi = 0;
+        for (size_t i = 0; i < n; ++i)
+            if (dm[i] > best) { best = dm[i]; bi = i; }
+        cur = bi;
+        out[t] = cur;
+    }
+    free(dm);
+    free(nb);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * kd-line tree build.  Follows src/_ext/KDTreeBase.h:84-207 + src/_ext/KDLineTree.h:37-39,87-92.
  * Works on a permuted row copy q[n][d] and the permutation perm[n] (perm[pos] = original id).

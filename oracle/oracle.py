@@ -1,7 +1,7 @@
 """ctypes front-end of the C oracle (oracle/fps_oracle.c) and loader of the compiled reference.
 
 TEST INFRASTRUCTURE ONLY.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
-``--impl reference`` legs may import this module; fpsample_b200 never does (tests/test_layout.py
+``--impl reference`` legs may import this module; fpsample_b200 never does (tests/test_host.py
 greps for it).  Parity pinning: see the header of fps_oracle.c.
 """
 from __future__ import annotations
@@ -42,6 +42,8 @@ def _load():
         L.oracle_certify_fps.argtypes = [fp, sz, sz, sz, szp, sz, ctypes.c_int, ctypes.c_int, szp]
         L.oracle_fps_npdu.argtypes = [fp, sz, sz, sz, sz, sz, szp]
         L.oracle_fps_npdu.restype = ctypes.c_int
+        L.oracle_fps_npdu_kdtree.argtypes = [fp, sz, sz, sz, sz, sz, szp]
+        L.oracle_fps_npdu_kdtree.restype = ctypes.c_int
         for f in (L.oracle_fps_vanilla, L.oracle_kdline_build, L.oracle_kdline_sample,
                   L.oracle_kdline_sample_eager, L.oracle_certify_fps):
             f.restype = ctypes.c_int
@@ -93,6 +95,15 @@ def kdline_build(pc, h):
                                      box.ctypes.data, ctypes.addressof(nl))
     _check(rc, "oracle_kdline_build")
     return perm, bounds[: nl.value + 1].copy(), box[: nl.value].copy()
+
+
+def fps_npdu_kdtree(pc, n_samples, k, start=0):
+    """Oracle twin of fpsample._fpsample._fps_npdu_kdtree_sampling (k-nearest-neighbour heuristic, src/lib.cpp:369-465)."""
+    pc = _f32(pc)
+    out = np.empty(n_samples, dtype=np.uint64)
+    rc = _load().oracle_fps_npdu_kdtree(pc.ctypes.data, pc.shape[0], pc.shape[1], n_samples, k, start, out.ctypes.data)
+    _check(rc, "oracle_fps_npdu_kdtree")
+    return out
 
 
 def kdline(pc, k, h, start=0, return_stats=False):

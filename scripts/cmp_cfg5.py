@@ -35,8 +35,8 @@ for B in Bs:
         capi.set_tuning("COUNT", -1)
         got = do.cpu().numpy().astype(np.uint64)
         ok = all(np.array_equal(got[b + nreal * j], want[b]) for b in want for j in range((B - b + nreal - 1) // nreal) if b + nreal * j < B)
-        pts, pu, fl, early, tests, picks, clouds = [int(x) for x in cnt[:7]]
-        byt = pts * 4 * (d + 2)
+        pts, pu, fl, early, tests, picks, clouds, stored = [int(x) for x in cnt[:8]]
+        byt = pts * 4 * (d + 1) + stored * 4
         print(f"B={B} d={d} wpc={wpc}: build {best[0]:7.2f} ms sampling {best[1]:7.2f} ms -> {B / sum(best) * 1e3:7.0f} clouds/s | parity {'OK' if ok else 'MISMATCH'} | "
               f"per pick: {pts / max(picks, 1):.0f} pts scanned, {pu / max(picks, 1):.0f} point-updates, {fl / max(picks, 1):.2f} passes ({early / max(picks, 1):.2f} early) | "
               f"{byt / 1e9:.1f} GB algorithmic -> {byt / best[1] / 1e6:.0f} GB/s | {capi.last_plan().split(' + ')[-1][:110]}", flush=True)

@@ -28,14 +28,12 @@ for _ in range(reps):
     e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
 print(f"{wl} {algo} B={B}: min {min(ts):.3f} ms mean {sum(ts)/len(ts):.3f} ms -> {B/min(ts)*1e3:.1f} clouds/s | {capi.last_plan()}")
 if algo == "kdline" and "dist" in capi.last_plan():
-    os.environ["FPS_B200_DBG_DIST"] = "1"
-    o = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(o.ctypes.data)
+    o = capi.debug_counters(capi.DBG_ASYNC)
     it = max(int(o[0]), 1)
     if int(o[0]): print("  dist dbg (cluster 0, CTA 0): iterations %d picks/iter %.2f | per iteration: cand+send %.0f wait %.0f select %.0f tests %.0f flush %.0f = %.0f cyc | flushed buckets/iter (this CTA) %.2f items/iter %.2f" % (
         o[0], o[1] / it, o[2] / it, o[3] / it, o[4] / it, o[5] / it, o[6] / it, sum(int(x) for x in o[2:7]) / it, o[7] / it, o[8] / it))
 if algo == "kdline" and "kdline_grid" in capi.last_plan():
-    os.environ["FPS_B200_DBG_GRID"] = "1"
-    o = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(o.ctypes.data)
+    o = capi.debug_counters(capi.DBG_GRID)
     it = max(int(o[0]), 1)
     print("  grid dbg (CTA 0): rounds %d picks/round %.1f | cycles per round: apply+select %.0f merge+publish %.0f gather %.0f eligible+rank %.0f pairs %.0f out+rel %.0f = %.0f" % (
         o[0], o[1] / it, o[2] / it, o[3] / it, o[4] / it, o[5] / it, o[6] / it, o[7] / it, sum(int(x) for x in o[2:8]) / it))
@@ -44,8 +42,7 @@ if algo == "kdline" and "async" in capi.last_plan():
     d = capi.debug_counters(); it = max(d["iterations"], 1)
     print("  dbg:", d, "| per iteration:", {k: round(v / it, 1) for k, v in d.items() if k.startswith("cyc")}, "picks/iter %.2f" % (d["picks"] / it))
 if algo == "kdline" and "warp" in capi.last_plan():
-    os.environ["FPS_B200_DBG_WARP"] = "1"
-    out = np.zeros(16, dtype=np.uint64); capi.lib().fps_b200_debug_counters(out.ctypes.data)
+    out = capi.debug_counters(capi.DBG_WARP)
     it = max(int(out[0]), 1)
     if int(out[0]): print("  warp dbg (cloud 0): picks %d | per pick: test %.0f scan %.0f reduce %.0f argmax %.0f total %.0f cyc | buckets/pick %.2f groups/pick %.2f" % (
         out[0], out[1] / it, out[2] / it, out[3] / it, out[4] / it, out[7] / it, out[5] / it, out[6] / it))

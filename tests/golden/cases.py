@@ -108,6 +108,17 @@ CASES = [
     ("lidar_npdu", ("lidar", 21, 20000), "npdu", dict(k=2048, w=156, start=11)),
     ("dim12_npdu", ("uniform", 52, 2000, 12), "npdu", dict(k=300, w=100, start=12)),
     ("dup_npdu", ("dup", 10, 3), "npdu", dict(k=5, w=4, start=2)),
+    # --- SURVEY.md section 8(f) row 4, second half: fps_npdu_kdtree_sampling (k nearest neighbours, src/lib.cpp:369-465); w = k.
+    #     Generic clouds only: exact ties AT the k-th nearest distance are resolved by nanoflann's traversal order there ----
+    ("G0_npdukd", ("rand42", 4096, 3), "npdukd", dict(k=1024, w=64, start=0)),
+    ("cfg3_npdukd", ("uniform", 2000, 16384, 3), "npdukd", dict(k=2048, w=128, start=5)),
+    ("wide_npdukd", ("uniform", 70, 4099, 3), "npdukd", dict(k=1000, w=2000, start=0)),
+    ("full_npdukd", ("uniform", 71, 3000, 3), "npdukd", dict(k=3000, w=3000, start=3)),
+    ("over_npdukd", ("uniform", 74, 1500, 2), "npdukd", dict(k=200, w=10**6, start=1499)),
+    ("w1_npdukd", ("uniform", 72, 2000, 6), "npdukd", dict(k=300, w=1, start=5)),
+    ("lidar_npdukd", ("lidar", 21, 20000), "npdukd", dict(k=1024, w=312, start=11)),
+    ("dim12_npdukd", ("uniform", 52, 2000, 12), "npdukd", dict(k=300, w=100, start=12)),
+    ("d1_npdukd", ("uniform", 75, 5000, 1), "npdukd", dict(k=400, w=40, start=0)),
 ]
 
 CASE_BY_ID = {c[0]: c for c in CASES}

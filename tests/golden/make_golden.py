@@ -36,6 +36,8 @@ def main():
             idx = ref.fps_sampling(pc, p["k"], p["start"])
         elif call == "npdu":
             idx = ref._fps_npdu_sampling(pc, p["k"], p["w"], p["start"])   # the binding itself: the python wrapper rewrites w
+        elif call == "npdukd":
+            idx = ref._fps_npdu_kdtree_sampling(pc, p["k"], p["w"], p["start"])
         elif call == "kdtree":
             idx = ref.bucket_fps_kdtree_sampling(pc, p["k"], p["start"])
         else:

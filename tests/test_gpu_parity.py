@@ -35,6 +35,8 @@ def gpu_call(pc, call, p):
         return capi.kdtree(pc, p["k"], p["start"])
     if call == "npdu":
         return capi.npdu(pc, p["k"], p["w"], p["start"])
+    if call == "npdukd":
+        return capi.npdu_kdtree(pc, p["k"], p["w"], p["start"])
     return capi.kdline(pc, p["k"], p["h"], p["start"])
 
 
@@ -416,6 +418,32 @@ def test_npdu_matches_the_oracle_and_the_front_end_is_a_drop_in(oracle, golden):
         np.testing.assert_array_equal(fps.fps_npdu_sampling(pc, 100, w=10**6, start_idx=3), oracle.fps_npdu(pc, 100, 4095, 3))
 
 
+def test_npdu_kdtree_matches_the_oracle_and_the_front_end_is_a_drop_in(oracle, golden):
+    """fps_npdu_kdtree_sampling (second half): the k-nearest-neighbour heuristic of src/lib.cpp:369-465.
+    The GPU finds the k nearest by brute force + radix select; the oracle by brute force + sort; both are pinned to the
+    compiled reference (nanoflann) by the golden cases.  Clouds in general position only (see include/fps_b200.h on ties)."""
+    for n, d, k, w, s, gen in [(4096, 3, 1024, 64, 0, "u"), (3000, 6, 500, 33, 7, "u"), (20000, 3, 700, 300, 5, "l"), (1000, 1, 1000, 17, 999, "u"),
+                               (50000, 3, 300, 2000, 1, "u"), (2500, 12, 400, 2499, 3, "u"), (600, 2, 100, 600, 0, "u"), (70000, 3, 200, 70, 9, "u")]:
+        pc = {"u": lambda: synth.uniform(n + d, n, d), "l": lambda: synth.lidar(n, n)}[gen]()
+        got = capi.npdu_kdtree(pc, k, w, s)
+        assert "npdu_knn_kernel" in capi.last_plan(), capi.last_plan()
+        np.testing.assert_array_equal(got, oracle.fps_npdu_kdtree(pc, k, w, s), err_msg=str((n, d, k, w, s, gen)))
+    pcs = synth.uniform_batch(8800, 40, 5000, 3)
+    st = (np.arange(40) * 97) % 5000
+    got = capi.npdu_kdtree_batch(pcs, 256, 80, st, devices=[0])
+    for b in range(0, 40, 3):
+        np.testing.assert_array_equal(got[b], oracle.fps_npdu_kdtree(pcs[b], 256, 80, int(st[b])))
+    np.random.seed(42)
+    pc = np.random.rand(4096, 3)
+    out = fps.fps_npdu_kdtree_sampling(pc, 1024, start_idx=0)          # default: n / n_samples * 16 = 64 neighbours
+    assert out.dtype == np.uint64 and out.shape == (1024,)
+    np.testing.assert_array_equal(out, golden["G0_npdukd"])
+    with pytest.warns(UserWarning, match="k is too large"):            # src/fpsample/__init__.py:136-138
+        np.testing.assert_array_equal(fps.fps_npdu_kdtree_sampling(pc, 100, w=10**6, start_idx=3), oracle.fps_npdu_kdtree(pc, 100, 4096, 3))
+    with pytest.raises(NotImplementedError):                            # src/lib.cpp:385-390
+        fps._fps_npdu_kdtree_sampling(pc.astype(np.float32), 10, 5, np.array([1, 2], dtype=np.uint64))
+
+
 def test_device_pointer_entries(oracle):
     import torch
     B, n, d, k, h = 6, 5000, 3, 400, 5
@@ -547,7 +575,7 @@ def test_cfg5_production_plan(d, B, ncheck, oracle):
     for b in sorted({0, B - 1} | set(int(x) for x in rng.integers(0, B, ncheck - 2))):
         np.testing.assert_array_equal(got[b], oracle.kdline(pcs[b], k, h, 0), err_msg=f"cloud {b}: {plan}")
     # the shard one of eight GPUs gets takes the same kernel with 4 warps per cloud; the full batch's one-warp teams are
-    # forced onto a slice of it (the planner picks them from ~2000 clouds per GPU on)
+    # forced onto a slice of it too (a knob: they buy nothing over two-warp teams)
     if d == 3:
         shard = capi.kdline_batch(pcs[:512], k, h, devices=[0])
         assert "kdline_stream_kernel" in capi.last_plan() and "WPC=4" in capi.last_plan(), capi.last_plan()
@@ -567,7 +595,8 @@ def test_executed_work_counters_of_the_streaming_sampler(oracle):
         got = capi.kdline_batch(pcs, k, h, devices=[0])
         assert "kdline_stream_kernel" in capi.last_plan(), capi.last_plan()
         cnt = capi.debug_counters(capi.DBG_STREAM)
-    pts, pu, passes, early, tests, picks, clouds = [int(x) for x in cnt[:7]]
+    pts, pu, passes, early, tests, picks, clouds, stored = [int(x) for x in cnt[:8]]
+    assert 0 < stored <= pts
     assert clouds == B and picks == B * (k - 1) and tests == picks * 2**h
     want_pu = 0
     for b in range(B):

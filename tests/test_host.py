@@ -131,9 +131,24 @@ def test_c_abi_return_codes_like_reference():
         fps._fpsample._bucket_fps_kdline_sampling(pc9, 4, 2, 0)
 
 
-def test_out_of_scope_entries_say_so():
-    with pytest.raises(NotImplementedError, match="outside the accelerated hot path"):
-        fps.fps_npdu_kdtree_sampling(PC, 10)   # needs nanoflann's kNN: the one reference entry that stays out of scope
+def test_every_reference_entry_point_exists():
+    """src/fpsample/__init__.py:209-217: all five public functions of the reference are there, with its signatures"""
+    import inspect
+    want = {"fps_sampling": ["pc", "n_samples", "start_idx"],
+            "fps_npdu_sampling": ["pc", "n_samples", "w", "start_idx"],
+            "fps_npdu_kdtree_sampling": ["pc", "n_samples", "w", "start_idx"],
+            "bucket_fps_kdtree_sampling": ["pc", "n_samples", "start_idx"],
+            "bucket_fps_kdline_sampling": ["pc", "n_samples", "h", "start_idx"]}
+    for name, params in want.items():
+        assert list(inspect.signature(getattr(fps, name)).parameters) == params, name
+        assert name in fps.__all__
+    with pytest.raises(AssertionError):
+        fps.fps_npdu_kdtree_sampling(PC, 10**9)
+    with pytest.warns(UserWarning, match="k is too large"):   # src/fpsample/__init__.py:136-138 (the cap is n_pts here, n_pts - 1 in the index-window variant)
+        try:
+            fps.fps_npdu_kdtree_sampling(PC, 10, w=10**9, start_idx=0)
+        except RuntimeError:
+            pass   # no GPU in the CPU suite: the call itself fails loudly after the front-end did its part
 
 
 @pytest.mark.skipif(HAVE_GPU, reason="checks the no-GPU behaviour")

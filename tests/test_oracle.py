@@ -26,6 +26,8 @@ def run_oracle(O, pc, call, p):
         return O.kdtree(pc, p["k"], p["start"])
     if call == "npdu":
         return O.fps_npdu(pc, p["k"], p["w"], p["start"])
+    if call == "npdukd":
+        return O.fps_npdu_kdtree(pc, p["k"], p["w"], p["start"])
     return O.kdline(pc, p["k"], p["h"], p["start"])
 
 
