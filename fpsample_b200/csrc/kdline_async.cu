@@ -405,12 +405,13 @@ __global__ void __launch_bounds__(MAXT, 1) kdline_async_kernel(AsyncArgs a) {
                     for (u32 r = 0; r <= CPW; ++r) {
                         const u64 wk = warp_max_key(kk);
                         if (r == 0) wthr = __uint_as_float((u32)(wk >> 32));
-                        // the lane holding the key publishes it itself (EXACT keys are unique; INFLIGHT keys may repeat:
-                        // the lanes then write the same key, and an INFLIGHT candidate only ever blocks what sorts behind it)
+                        // the lane holding the key publishes it (EXACT keys are unique; INFLIGHT keys may repeat: the lowest of
+                        // those lanes writes, and an INFLIGHT candidate only ever blocks what sorts behind it)
                         const bool me = kk == wk && wk != 0ull;
+                        const u32 first_me = (u32)__ffs(__ballot_sync(FULL, me)) - 1u;
                         if (r < CPW) {
                             ACand &e = cand[par * A_NC + warp * CPW + r];
-                            if (me) {
+                            if (me && lane == first_me) {   // one writer: the lowest of the lanes that tie
                                 e.key = wk;
                                 e.bucket = warp * 32 + lane;
                             } else if (wk == 0ull && lane == 0) {

@@ -105,7 +105,8 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   /
 // stores: a warp access is 512 contiguous bytes per component); a bucket pass is cut into runs of chunks, one run per warp.
 // Per pick the team meets at TWO named barriers: after the tests (pending entries + the list of buckets to pass over) and
 // after the passes (one partial maximum per warp and bucket).  Everything after that is done by every warp for itself --
-// merging the partial maxima into its own copy of the bucket maxima, the arg-max over them -- so no third exchange is needed.
+// merging the partial maxima into its own copy of the bucket maxima, the arg-max over them -- so no third exchange is needed
+// (checked with compute-sanitizer racecheck, profiles/r02_sanitizer_racecheck.log).
 template <int DIM, int WPC, int BPL>
 __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 tm /* shared address */, u32 cnt_s) {
     constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
@@ -119,13 +120,14 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     float *dis = reinterpret_cast<float *>(rg) + (size_t)dim * npad;
 
     // team shared memory (32-bit shared addresses): pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} |
-    // max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted per group) | part[2][S_MAXF][WPC]
+    // max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted per group) | part[2][S_MAXF][WPC] | fslot[WPC]
     const u32 pend = tm;
     const u32 brec = tm + R * SP * PRB;
     const u32 bmcs = brec + SP * 16;
     const u32 fmask = bmcs + SP * PRB;
     const u32 flist = fmask + ((NW + 3) & ~3u) * 4;
     const u32 part = flist + SP * 4;
+    const u32 fslot = part + 2 * S_MAXF * WPC * S_REC + tw * PRB;   // one per warp
 
     // ---- distances start at FLT_MAX (Point.h:61-65); bucket boundaries to shared memory ------------------------------
     for (u32 p = (tw * 32 + lane) * 4; p < npad; p += WPC * 128)
@@ -224,6 +226,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         team_sync<WPC>(team);
 
         // ---- 2. bucket passes: every flushed bucket, this warp's run of chunks, all pending samples applied -----------------
+        u32 fm = 0, fq = S_NONE;   // the best maximum among the buckets passed over in THIS pick (value bits, position); its
+                                   // point is parked in this WARP's own slot: if it wins the arg-max, the coordinates come from there
         u32 pre[NW];   // flushed buckets up to and including group w
         {
             u32 acc = 0;
@@ -388,24 +392,35 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     tmax[s] = hit ? __uint_as_float(m) : tmax[s];
                     tpos[s] = hit ? qpos : tpos[s];
                 }
-                if (mineb) {
+                if (qpos != S_NONE && (fq == S_NONE || m > fm || (m == fm && qpos < fq))) {   // (uniform over the warp)
+                    fm = m, fq = qpos;
+                    if (lane == 0) {
+                        const float4 c0v = s_lds128(src + 16);
+                        s_sts128(fslot, c0v.x, c0v.y, c0v.z, c0v.w);
+                        if constexpr (DIM > 4) {
+                            const float4 c1v = s_lds128(src + 32);
+                            s_sts128(fslot + 16, c1v.x, c1v.y, c1v.z, c1v.w);
+                        }
+                    }
+                }
+                if (mineb && (b >> 5) / BPL == tw) {   // the owner: its tests compare against the new maximum, its list is empty again
                     const float4 c0v = s_lds128(src + 16);
                     float4 c1v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if constexpr (DIM > 4) c1v = s_lds128(src + 32);
-                    // the max point's coordinates, for whoever wins the arg-max (every warp writes the same bits)
+                    // the max point's coordinates for a LATER pick's arg-max (single writer; this pick's winner, if it is one of
+                    // the buckets just passed over, is taken from fc above, so nobody reads this entry before the next barrier)
                     s_sts128(bmcs + b * PRB, c0v.x, c0v.y, c0v.z, c0v.w);
                     if constexpr (DIM > 4) s_sts128(bmcs + b * PRB + 16, c1v.x, c1v.y, c1v.z, c1v.w);
-                    const bool own = (b >> 5) / BPL == tw;   // the owner: its tests compare against the new maximum, its list is empty again
                     const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
 #pragma unroll
                     for (int j = 0; j < BPL; ++j) {
-                        const bool hit = own && ((b >> 5) % BPL) == (u32)j;
+                        const bool hit = ((b >> 5) % BPL) == (u32)j;
                         if constexpr (WPC != 1) S_OWNMAX(j) = hit ? __uint_as_float(m) : S_OWNMAX(j);
                         np[j] = hit ? 0u : np[j];
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) bmc[j][c] = hit ? cc[c] : bmc[j][c];
                     }
-                    if (own) sts32(brec + b * 16 + 8, 0u);
+                    sts32(brec + b * 16 + 8, 0u);
                 }
             }
             bp ^= 1u;
@@ -425,11 +440,13 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         cur = __reduce_min_sync(FULL, mine);
         const u32 srcl = __ffs(__ballot_sync(FULL, mine == cur)) - 1;   // positions are unique: exactly one lane
         const u32 bw = __shfl_sync(FULL, sb * 32 + lane, srcl);
-        __syncwarp();   // this warp's own copy of the winner's coordinates (written by another lane, above)
-        {
-            const float4 c0v = s_lds128(bmcs + bw * PRB);
+        {   // the winner's point: a bucket passed over in this pick -> this warp's own slot (written by lane 0 above); an older
+            // maximum -> the table its owner filled before an earlier barrier
+            __syncwarp();
+            const u32 from = cur == fq ? fslot : bmcs + bw * PRB;
+            const float4 c0v = s_lds128(from);
             float4 c1v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if constexpr (DIM > 4) c1v = s_lds128(bmcs + bw * PRB + 16);
+            if constexpr (DIM > 4) c1v = s_lds128(from + 16);
             const float cc[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
 #pragma unroll
             for (int c = 0; c < DIM; ++c) r[c] = cc[c];
@@ -494,7 +511,7 @@ static size_t stream_team_bytes(int dimp, u32 wpc, u32 bpl, u32 R) {
     const size_t SP = 32u * wpc * bpl, PRB = (size_t)((dimp + 3) / 4) * 16, NW = wpc * bpl;
     size_t b = R * SP * PRB;
     b += SP * 16 + SP * PRB + ((NW + 3) & ~(size_t)3) * 4 + SP * 4;
-    b += 2 * S_MAXF * wpc * S_REC;
+    b += 2 * S_MAXF * wpc * S_REC + wpc * PRB;
     return (b + 15) & ~(size_t)15;
 }
 
