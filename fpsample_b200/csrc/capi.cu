@@ -72,6 +72,7 @@ static const KnobDesc kKnobs[] = {
     {"WARP_TMEM", nullptr, &Tuning::warp_tmem}, {"WARP_LAZY", nullptr, &Tuning::warp_lazy},
     {"WARP_HYBRID", nullptr, &Tuning::warp_hybrid}, {"WARP_GLOBAL_MINB", &Tuning::warp_global_minb, nullptr},
     {"KDSMALL", nullptr, &Tuning::kdsmall},     {"STREAM_WARPS", nullptr, &Tuning::stream_warps},
+    {"PSUM", nullptr, &Tuning::psum},
     {"COUNT", nullptr, &Tuning::count},         {"PREFETCH", nullptr, &Tuning::prefetch},
 };
 static bool set_knob(const char *name, long v) {
@@ -1290,15 +1291,15 @@ int fps_b200_kdline_build_dev(const float *d_points, size_t B, size_t n, size_t 
 }
 
 int fps_b200_seqsum_dev(const float *d_values, size_t n, float *d_sum, uint32_t *d_fast_tiles, int tile, void *stream) {
-    if (!d_values || !d_sum || n == 0 || (tile != 256 && tile != 512)) {
-        set_err("bad argument: need values/sum non-null, n >= 1, tile 256 or 512");
+    if (!d_values || !d_sum || n == 0 || (tile != 256 && tile != 512 && tile != -512)) {
+        set_err("bad argument: need values/sum non-null, n >= 1, tile 256, 512 or -512 (two-phase)");
         return FPS_ERR_ARG;
     }
     if (n_sms_current(nullptr) <= 0) {
         set_err("current device is not a usable sm_100 device; there is no CPU fallback");
         return FPS_ERR_NO_DEVICE;
     }
-    CK(launch_seqsum(d_values, n, d_sum, d_fast_tiles, tile / 32, static_cast<cudaStream_t>(stream)));
+    CK(launch_seqsum(d_values, n, d_sum, d_fast_tiles, tile < 0 ? -1 : tile / 32, static_cast<cudaStream_t>(stream)));
     return FPS_OK;
 }
 

@@ -33,6 +33,7 @@ struct GBArgs {
     unsigned char *aux;   // per cloud: A0[S] A1[S] A2[S] A3[S] nitems[S] ibase[S+1 -> pad] part[wmax]
     size_t aux_stride;
     u32 B, n, npad, dim, h, S, nlo_pad, wmax, lvl;
+    u32 psum, ntmax;   // this level's split values come from the two-phase sum (gb_ptiles / gb_psum_a / gb_psum_b); tiles per cloud at most
 };
 
 struct GBView {
@@ -40,6 +41,9 @@ struct GBView {
     u32 *scr, *perm, *nlo;
     int *box;
     u32 *A0, *A1, *A2, *A3, *nitems, *ibase, *part;
+    u32 *ptb;          // two-phase sum: first tile of every node of the level (+ total)
+    double *dsum;      // double-precision sum of every 512-element tile (only to GUESS the binade the running sum is in)
+    SeqTileRec *recs;  // the tile's integer record under that guess (seqsum.cuh)
 };
 
 __device__ __forceinline__ GBView gb_view(const GBArgs &a, u32 cloud) {
@@ -58,6 +62,14 @@ __device__ __forceinline__ GBView gb_view(const GBArgs &a, u32 cloud) {
     v.nitems = ax + 4 * a.S;
     v.ibase = ax + 5 * a.S;
     v.part = ax + 6 * a.S + 32;
+    unsigned char *px = reinterpret_cast<unsigned char *>(v.part + a.wmax);
+    px += (16 - (reinterpret_cast<uintptr_t>(px) & 15)) & 15;
+    v.ptb = reinterpret_cast<u32 *>(px);
+    px += ((size_t)(a.S + 4) * 4 + 15) & ~(size_t)15;
+    v.dsum = reinterpret_cast<double *>(px);
+    px += (size_t)a.ntmax * 8;
+    px += (16 - (reinterpret_cast<uintptr_t>(px) & 15)) & 15;
+    v.recs = reinterpret_cast<SeqTileRec *>(px);
     return v;
 }
 
@@ -88,6 +100,172 @@ __global__ void __launch_bounds__(256) gb_rootbox(GBArgs a) {
     if (s0 >= a.n) return;
     const u32 s1 = min(a.n, s0 + GB_WCH);
     box_range<DIM>(v.q, a.npad, a.dim, s0, s1, a.n, v.box, v.box);
+}
+
+// ---- two-phase sequential sum for LONG columns (one huge cloud: BASELINE.json cfg 4) ---------------------------------------
+// The split value is a strictly sequential binary32 sum (KDTreeBase.h:151-158): one dependent FADD per element, 1 M elements
+// at the root.  seqsum.cuh turns a 512-element tile into an integer addition when the running sum stays inside one binade,
+// but a warp still walks the tiles one after the other (1.6 cycles per element).  Here the expensive part of every tile is
+// computed by the WHOLE GRID before the walk, under a guess of the binade the running sum will be in when it gets there:
+//   gb_ptiles  one warp per cloud: tiles per node of this level, exclusive prefix
+//   gb_psum_a  one warp per tile: the tile's sum in double precision
+//   gb_psum_b  one warp per tile: guess = binade of (double prefix of the tiles before it), the tile's integer record
+//              under that guess (seq_sum_tile_record: increments for an even / odd incoming sum, prefix bounds)
+//   gb_split   one warp per node walks the records: ~12 dependent instructions per tile instead of ~800; a tile whose
+//              guess was wrong, or that leaves its binade, or that holds an element too large for the integer model is
+//              summed by the plain chain.  The result is the sequential sum bit for bit either way.
+constexpr u32 PS_TILE = 512;
+
+__global__ void __launch_bounds__(32) gb_ptiles(GBArgs a) {
+    const u32 cloud = blockIdx.x, nn = 1u << a.lvl, stride = a.S >> a.lvl, lane = lane_id();
+    GBView v = gb_view(a, cloud);
+    u32 run = 0;
+    for (u32 j0 = 0; j0 < nn; j0 += 32) {
+        const u32 j = j0 + lane;
+        u32 x = 0;
+        if (j < nn) {
+            const u32 cnt = v.nlo[j * stride + stride] - v.nlo[j * stride];
+            x = cnt >= 2 ? cnt / PS_TILE : 0u;
+        }
+        u32 inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(FULL, inc, o);
+            if ((int)lane >= o) inc += y;
+        }
+        if (j < nn) v.ptb[j] = run + inc - x;
+        run += __shfl_sync(FULL, inc, 31);
+    }
+    if (lane == 0) v.ptb[nn] = run;
+}
+
+// tile wi of the cloud -> (node, tile of the node, first element); false if there is no such tile
+__device__ __forceinline__ bool gb_ptile(const GBArgs &a, const GBView &v, u32 wi, u32 *node, u32 *r, const float **src) {
+    const u32 nn = 1u << a.lvl, stride = a.S >> a.lvl;
+    if (wi >= v.ptb[nn]) return false;
+    u32 l = 0, rr = nn;   // last node with ptb[j] <= wi
+    while (rr - l > 1) {
+        const u32 m = (l + rr) >> 1;
+        if (v.ptb[m] <= wi) l = m;
+        else rr = m;
+    }
+    const u32 idx = l * stride;
+    const int *b = v.box + (size_t)idx * 2 * a.dim;
+    u32 sd = 0;
+    float span = 0.0f;
+    for (u32 c = 0; c < a.dim; ++c) {   // the split dimension, as gb_split finds it (KDTreeBase.h:160-179)
+        const float s = __fsub_rn(ord2f(b[a.dim + c]), ord2f(b[c]));
+        if (s > span) {
+            span = s;
+            sd = c;
+        }
+    }
+    *node = l;
+    *r = wi - v.ptb[l];
+    *src = v.q + (size_t)sd * a.npad + v.nlo[idx] + (size_t)(wi - v.ptb[l]) * PS_TILE;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) gb_psum_a(GBArgs a) {
+    const u32 cloud = blockIdx.y, lane = lane_id();
+    GBView v = gb_view(a, cloud);
+    const u32 wi = blockIdx.x * 8 + warp_id();
+    u32 node, r;
+    const float *src;
+    if (!gb_ptile(a, v, wi, &node, &r, &src)) return;
+    double acc = 0.0;
+#pragma unroll
+    for (u32 k = 0; k < PS_TILE / 32; ++k) acc += (double)src[k * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (lane == 0) v.dsum[wi] = acc;
+}
+
+__global__ void __launch_bounds__(256) gb_psum_b(GBArgs a) {
+    __shared__ __align__(16) float tile[8][PS_TILE];
+    const u32 cloud = blockIdx.y, lane = lane_id(), warp = warp_id();
+    GBView v = gb_view(a, cloud);
+    const u32 wi = blockIdx.x * 8 + warp;
+    u32 node, r;
+    const float *src;
+    if (!gb_ptile(a, v, wi, &node, &r, &src)) return;
+#pragma unroll
+    for (u32 k = 0; k < PS_TILE / 32; ++k) tile[warp][k * 32 + lane] = src[k * 32 + lane];
+    // the sum of everything before this tile, well enough to know its binade
+    double pre = 0.0;
+    const double *ds = v.dsum + v.ptb[node];
+    for (u32 t = lane; t < r; t += 32) pre += ds[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(FULL, pre, o);
+    const u32 ef = (__float_as_uint((float)pre) >> 23) & 0xffu;
+    __syncwarp();
+    int t0 = 0, t1 = 0, lo = 0, hi = 0;
+    const bool ok = seq_sum_tile_record<PS_TILE / 32>(smem_u32(tile[warp]), ef, t0, t1, lo, hi);
+    if (lane == 0) {
+        SeqTileRec rec;
+        rec.ef = ok ? ef : 0u;
+        rec.tot0 = t0, rec.tot1 = t1, rec.lo = lo, rec.hi = hi;
+        rec.pad[0] = rec.pad[1] = rec.pad[2] = 0u;
+        v.recs[wi] = rec;
+    }
+}
+
+// the walk over the records of one node (one warp; `ring`: 512 floats of warp-private shared memory for the chain fall-back).
+// While consecutive records agree on the binade the running sum is kept as the INTEGER k (sum = k * ulp): a tile is then a
+// parity select, one integer add and the bound check -- no float <-> int conversion on the chain.
+__device__ __forceinline__ float seq_sum_records(const float *src, u32 count, const SeqTileRec *recs, float *ring) {
+    const u32 lane = lane_id(), ntile = count / PS_TILE;
+    float sum = 0.0f;
+    bool fast = false;   // k / cef hold the running sum
+    u32 cef = 0;
+    int k = 0;
+    auto to_float = [&]() {
+        if (fast) sum = __fmul_rn(__int2float_rn(k), __uint_as_float((cef - 23u) << 23));   // exact
+        fast = false;
+    };
+    for (u32 t0 = 0; t0 < ntile; t0 += 32) {
+        SeqTileRec r;
+        r.ef = 0u, r.tot0 = r.tot1 = r.lo = r.hi = 0;
+        if (t0 + lane < ntile) r = recs[t0 + lane];
+        const u32 nb = min(32u, ntile - t0);
+        for (u32 j = 0; j < nb; ++j) {
+            const u32 ef = __shfl_sync(FULL, r.ef, j);
+            const int a0 = __shfl_sync(FULL, r.tot0, j), a1 = __shfl_sync(FULL, r.tot1, j);
+            const int lo = __shfl_sync(FULL, r.lo, j), hi = __shfl_sync(FULL, r.hi, j);
+            if (!fast || ef != cef) {   // (re-)enter the integer form in this record's binade, if the sum really is in it
+                to_float();
+                if (ef != 0u && ((__float_as_uint(sum) >> 23) & 0xffu) == ef) {
+                    k = __float2int_rn(__fmul_rn(sum, __uint_as_float((277u - ef) << 23)));   // exact, 2^23 <= |k| < 2^24
+                    cef = ef;
+                    fast = true;
+                }
+            }
+            bool ok = fast;
+            if (ok) {
+                const int klo = k + lo, khi = k + hi;
+                ok = k > 0 ? (klo > (1 << 23) && khi < (1 << 24)) : (khi < -(1 << 23) && klo > -(1 << 24));
+            }
+            if (ok) {
+                k += (k & 1) ? a1 : a0;   // (the bounds include the tile's last prefix: k stays inside the binade)
+                continue;
+            }
+            to_float();
+            const float *ts = src + (size_t)(t0 + j) * PS_TILE;   // the plain chain over this tile
+#pragma unroll
+            for (u32 kk = 0; kk < PS_TILE / 32; ++kk) ring[kk * 32 + lane] = ts[kk * 32 + lane];
+            __syncwarp();
+            sum = sq_chain16(smem_u32(ring), PS_TILE, sum);
+            __syncwarp();
+        }
+    }
+    to_float();
+    // tail (< 512 values): lanes fetch 32 at a time, the chain consumes them through shuffles
+    for (u32 i = ntile * PS_TILE; i < count; i += 32) {
+        const float x = (i + lane < count) ? src[i + lane] : 0.0f;
+        const u32 m = min(32u, count - i);
+        for (u32 j = 0; j < m; ++j) sum = __fadd_rn(sum, __shfl_sync(FULL, x, j));
+    }
+    return sum;
 }
 
 // ---- gb_split: one warp per node ---------------------------------------------------------------------------------
@@ -124,7 +302,8 @@ __global__ void __launch_bounds__(128) gb_split(GBArgs a) {
             sd = c;
         }
     }
-    const float sum = seq_sum_tma(v.q + (size_t)sd * a.npad + lo, count, ring[warp_id()], bars[warp_id()], phase);
+    const float sum = a.psum ? seq_sum_records(v.q + (size_t)sd * a.npad + lo, count, v.recs + v.ptb[j], ring[warp_id()])
+                             : seq_sum_tma(v.q + (size_t)sd * a.npad + lo, count, ring[warp_id()], bars[warp_id()], phase);
     const float val = __fdiv_rn(sum, __uint2float_rn(count));
     if (lane == 0) {
         v.A0[j] = __float_as_uint(val);
@@ -329,10 +508,13 @@ static u32 gb_wmax(size_t n, size_t S) {
     return (u32)((w + GB_WPB - 1) / GB_WPB * GB_WPB);
 }
 
+static u32 gb_ntmax(size_t n) { return (u32)(n / PS_TILE + 1); }
+
 size_t kd_gridbuild_aux_bytes(size_t n, size_t dim, size_t h) {
     (void)dim;
     const size_t S = (size_t)1 << h;
     size_t b = (6 * S + 32 + gb_wmax(n, S)) * 4;
+    b += 16 + (((S + 4) * 4 + 15) & ~(size_t)15) + (size_t)gb_ntmax(n) * 8 + 16 + (size_t)gb_ntmax(n) * sizeof(SeqTileRec);   // two-phase sum
     return (b + 255) & ~(size_t)255;
 }
 
@@ -368,6 +550,8 @@ cudaError_t launch_kd_gridbuild(const float *pts, unsigned char *region, size_t 
     a.S = 1u << h;
     a.nlo_pad = (a.S + 1 + 31) & ~31u;
     a.wmax = gb_wmax(n, a.S);
+    a.ntmax = gb_ntmax(n);
+    a.psum = 0;
     a.lvl = 0;
     const u32 stage_blocks = (u32)std::min<size_t>(((size_t)n * dim + 1023) / 1024, 1024);
     gb_stage<<<dim3(stage_blocks, B), 256, 0, st>>>(a);
@@ -378,6 +562,15 @@ cudaError_t launch_kd_gridbuild(const float *pts, unsigned char *region, size_t 
     for (u32 lvl = 0; lvl < h; ++lvl) {
         a.lvl = lvl;
         const u32 nodes = B << lvl;
+        // few long columns (the top levels of one huge cloud): the whole grid prepares the tiles of the sequential sum first
+        a.psum = (tuning().psum != 0 && (n >> lvl) >= 16384 && (size_t)nodes <= 4 * 148) ? 1u : 0u;
+        if (a.psum) {
+            const dim3 gt((a.ntmax + 7) / 8, B);
+            gb_ptiles<<<B, 32, 0, st>>>(a);
+            gb_psum_a<<<gt, 256, 0, st>>>(a);
+            gb_psum_b<<<gt, 256, 0, st>>>(a);
+            for (int i = 0; i < 3; ++i) count_launch();
+        }
         gb_split<<<(nodes + 3) / 4, 128, 0, st>>>(a);
         gb_items<<<B, 32, 0, st>>>(a);
         gb_count<<<gi, 256, 0, st>>>(a);

@@ -150,6 +150,98 @@ __device__ __forceinline__ bool seq_sum_tile(u32 a, float &s, u32 &hint) {
     return true;
 }
 
+
+// ---- the same tile, WITHOUT knowing the incoming sum: a record for the two-phase sum of long columns (kdbuild.cu) ---------
+// Under the hypothesis that the running sum enters the tile inside binade `ef` (biased exponent) and never leaves it, the
+// tile adds an integer number of ulps that depends on the incoming sum only through its PARITY (the first exact tie):
+// tot0 for an even, tot1 for an odd incoming k.  lo / hi bound every partial sum of the tile relative to the incoming k
+// (with the one-unit slack of seq_sum_tile), so the consumer -- which walks the tiles in order with the true running sum --
+// accepts the record iff its sum really is in binade ef and k + lo, k + hi stay inside (2^23, 2^24); otherwise it runs
+// the plain chain over the tile.  Either way the result is the sequential sum, bit for bit; the hypothesis only decides
+// how fast.  Returns false when the tile does not fit the integer model at all (an element too large for the binade).
+struct SeqTileRec {
+    u32 ef;
+    int tot0, tot1, lo, hi;
+    u32 pad[3];
+};
+template <int EPL>
+__device__ __forceinline__ bool seq_sum_tile_record(u32 a, u32 ef, int &tot0, int &tot1, int &LO, int &HI) {
+    static_assert(EPL % 4 == 0 && EPL >= 4 && EPL <= 32, "a lane reads whole float4s");
+    const u32 lane = lane_id();
+    if (ef < 24u || ef == 255u) return false;
+    const float scale = __uint_as_float((277u - ef) << 23);          // 1 / u = 2^(150 - ef)
+    int sm = 0, mn = 0x7fffffff, mx = (int)0x80000000, dlt = 0;
+    u32 q = 0;                                                       // parity of the running k, "even on entry" of the lane
+    bool seen = false, bad = false;
+    const u32 base = a + lane * (u32)(EPL * 4);
+#pragma unroll
+    for (int t = 0; t < EPL / 4; ++t) {
+        const float4 f = sq_lds128(base + 16u * t);
+        const float x[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float v = __fmul_rn(x[c], scale);
+            bad = bad || !(fabsf(v) < 524288.0f);                    // also catches nan
+            const float tm = __fadd_rn(v, 12582912.0f);
+            const int r = (__float_as_int(tm) & 0x7fffff) - 0x400000;
+            const float d = __fsub_rn(v, __fsub_rn(tm, 12582912.0f));   // exact
+            const bool tie = fabsf(d) == 0.5f;
+            const int alt = r + (d > 0.0f ? 1 : -1);                 // the other neighbour of a tie
+            const int inc = (tie && q) ? alt : r;                    // r is the even neighbour: right when k is even
+            if (tie && !seen) {
+                dlt = (q ? r : alt) - inc;                           // what "odd on entry" adds here instead
+                seen = true;
+            }
+            q = tie ? 0u : (q ^ (u32)(inc & 1));
+            sm += inc;
+            mn = min(mn, sm);
+            mx = max(mx, sm);
+        }
+    }
+    if (__any_sync(FULL, bad)) return false;
+    // parity on entry of every lane, for an even (p0) and an odd (p1) incoming k: the last lane below with a tie fixes it
+    // for both, lanes without one flip it by their sum
+    const u32 C = __ballot_sync(FULL, seen), V = __ballot_sync(FULL, q & 1u);
+    const u32 below = (1u << lane) - 1u, cm = C & below;
+    u32 p0, p1, span;
+    if (cm) {
+        const u32 c = 31u - (u32)__clz(cm);
+        p0 = p1 = (V >> c) & 1u;
+        span = below & ~((2u << c) - 1u);
+    } else {
+        p0 = 0u, p1 = 1u;
+        span = below;
+    }
+    const u32 flip = (u32)__popc(V & span) & 1u;
+    p0 ^= flip, p1 ^= flip;
+    const int sl0 = sm + (p0 ? dlt : 0), sl1 = sm + (p1 ? dlt : 0);
+    int x0 = sl0, x1 = sl1;   // inclusive prefix sums over lanes
+#pragma unroll
+    for (int dd = 1; dd < 32; dd <<= 1) {
+        const int y0 = __shfl_up_sync(FULL, x0, dd), y1 = __shfl_up_sync(FULL, x1, dd);
+        if ((int)lane >= dd) x0 += y0, x1 += y1;
+    }
+    const int off0 = x0 - sl0, off1 = x1 - sl1;
+    tot0 = __shfl_sync(FULL, x0, 31), tot1 = __shfl_sync(FULL, x1, 31);
+    LO = min(__reduce_min_sync(FULL, off0 + mn - 1), __reduce_min_sync(FULL, off1 + mn - 1));   // slack: the hypothesis a lane did not track
+    HI = max(__reduce_max_sync(FULL, off0 + mx + 1), __reduce_max_sync(FULL, off1 + mx + 1));
+    return true;
+}
+
+// the consumer side: apply one record to the running sum (warp-uniform); false = run the chain over the tile instead
+__device__ __forceinline__ bool seq_sum_apply_record(float &s, u32 ef, int tot0, int tot1, int lo, int hi) {
+    const u32 es = (__float_as_uint(s) >> 23) & 0xffu;
+    if (ef == 0u || es != ef) return false;
+    const float scale = __uint_as_float((277u - ef) << 23);
+    const float u = __uint_as_float((ef - 23u) << 23);
+    const int k_in = __float2int_rn(__fmul_rn(s, scale));            // exact, 2^23 <= |k_in| < 2^24
+    const int klo = k_in + lo, khi = k_in + hi;
+    const bool ok = k_in > 0 ? (klo > (1 << 23) && khi < (1 << 24)) : (khi < -(1 << 23) && klo > -(1 << 24));
+    if (!ok) return false;
+    s = __fmul_rn(__int2float_rn(k_in + ((k_in & 1) ? tot1 : tot0)), u);
+    return true;
+}
+
 // the whole sequential sum of `count` floats at shared address `a` (4-byte aligned), tiles of 32 * EPL where they apply
 template <int EPL>
 __device__ __forceinline__ float seq_sum_shared(u32 a, u32 count) {

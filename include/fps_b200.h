@@ -167,8 +167,9 @@ FPS_API int fps_b200_kdline_build_dev(const float *d_points, size_t B, size_t n,
 
 /* The kd build's split value (testing / inspection): d_sum[0] = the STRICTLY SEQUENTIAL binary32 sum of d_values[0..n)
  * (`float s = 0; for (...) s += x;`, src/_ext/KDTreeBase.h:151-158), evaluated by one warp through the tile-parallel code
- * of the build kernels (csrc/seqsum.cuh; tile = 256 or 512 elements).  d_fast_tiles (may be NULL) receives how many tiles
- * took the integer prefix-scan path instead of the dependent add chain. */
+ * of the build kernels (csrc/seqsum.cuh; tile = 256 or 512 elements; tile = -512: the two-phase form of the grid-wide build,
+ * where 512-element tiles are prepared in parallel under a guessed binade and one warp walks their records).  d_fast_tiles
+ * (may be NULL) receives how many tiles took the integer path instead of the dependent add chain. */
 FPS_API int fps_b200_seqsum_dev(const float *d_values, size_t n, float *d_sum, uint32_t *d_fast_tiles, int tile,
                         void *stream);
 
@@ -190,7 +191,7 @@ FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kerne
 FPS_API int fps_b200_debug_counters(int which, uint64_t *out16);
 /* Planner overrides (tests, experiments).  The library reads FPS_B200_<NAME> from the environment ONCE, at first use; after
  * that only this call changes a knob.  value -1 = the planner's own choice.  Names: GRID, GROUP, GRIDBUILD, VANILLA_KD, PIPE,
- * ZEROCOPY, GRID_ECAP, WARP, WARP_TMEM, WARP_LAZY, WARP_HYBRID, WARP_GLOBAL_MINB, KDSMALL, STREAM_WARPS, COUNT, PREFETCH. */
+ * ZEROCOPY, GRID_ECAP, WARP, WARP_TMEM, WARP_LAZY, WARP_HYBRID, WARP_GLOBAL_MINB, KDSMALL, STREAM_WARPS, COUNT, PREFETCH, PSUM. */
 FPS_API int fps_b200_set_tuning(const char *name, long value);
 /* Device-resident inputs of the host-pointer entries: the calling thread's NEXT call waits (on the device, through an event)
  * for the work queued on `stream` -- the stream that produced the points -- instead of the legacy default stream.  Nothing is

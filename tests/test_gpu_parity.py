@@ -366,8 +366,9 @@ def test_gpu_resident_arrays_through_the_python_api(oracle):
 
 def test_sequential_sum_tiles_are_bit_exact():
     """the split value is a strictly sequential binary32 sum (KDTreeBase.h:151-158); the build kernels evaluate it tile by
-    tile as an integer prefix scan (csrc/seqsum.cuh).  Bit-equal to numpy's sequential float32 accumulate on columns
-    that hit every branch: single-signed, zero-mean, exact ties, lattices, wild magnitudes, inf."""
+    tile as an integer prefix scan (csrc/seqsum.cuh), and for long columns in two phases: the tiles are prepared in parallel
+    under a guessed binade and one warp walks their records (tile = -512).  Bit-equal to numpy's sequential float32
+    accumulate on columns that hit every branch: single-signed, zero-mean, exact ties, lattices, wild magnitudes, inf."""
     import torch
     g = np.random.default_rng(77)
     n = 300_000
@@ -389,11 +390,13 @@ def test_sequential_sum_tiles_are_bit_exact():
         col = np.ascontiguousarray(col, dtype=np.float32)
         want = np.add.accumulate(col, dtype=np.float32)[-1]           # strictly sequential
         d = torch.from_numpy(col).cuda()
-        for tile in (256, 512):
+        for tile in (256, 512, -512):
             capi.seqsum_dev(d.data_ptr(), col.size, out.data_ptr(), fast.data_ptr(), tile, torch.cuda.current_stream().cuda_stream)
             got = out.cpu().numpy()[0]
             assert got.tobytes() == want.tobytes(), f"{name} tile={tile}: {got!r} != {want!r}"
             some_fast += int(fast.cpu().numpy()[0])
+            if tile == -512 and name in ("uniform", "quarters", "gauss"):
+                assert int(fast.cpu().numpy()[0]) > 0.5 * (col.size // 512), f"{name}: the two-phase sum fell back to the chain on most tiles"
     assert some_fast > 1000   # the scan path really ran
 
 
