@@ -96,6 +96,44 @@ __device__ __forceinline__ void sts128u(u32 a, u32 x, u32 y, u32 z, u32 w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 __device__ __forceinline__ float4 ldg128(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float2 s_lds64(u32 a) {
+    float2 f;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f.x), "=f"(f.y) : "r"(a));
+    return f;
+}
+__device__ __forceinline__ void s_sts64(u32 a, float x, float y) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(x), "f"(y) : "memory"); }
+
+// a pending-list entry = the sample's DIM coordinates: 16 bytes up to 4 dimensions, 24 for 6 (three 64-bit accesses: a third
+// more entries per bucket in the same shared memory, and 6-D clouds defer ~14 samples per pick), 32 for 8
+template <int DIM>
+struct PendEntry {
+    static constexpr u32 kBytes = DIM <= 4 ? 16u : DIM <= 6 ? 24u : 32u;
+    static __device__ __forceinline__ void store(u32 e, const float (&r)[DIM]) {
+        if constexpr (DIM <= 4) {
+            s_sts128(e, r[0], DIM > 1 ? r[DIM > 1 ? 1 : 0] : 0.f, DIM > 2 ? r[DIM > 2 ? 2 : 0] : 0.f, DIM > 3 ? r[DIM > 3 ? 3 : 0] : 0.f);
+        } else if constexpr (DIM <= 6) {
+            s_sts64(e, r[0], r[1]);
+            s_sts64(e + 8u, r[2], r[3]);
+            s_sts64(e + 16u, r[4], DIM > 5 ? r[DIM > 5 ? 5 : 0] : 0.f);
+        } else {
+            s_sts128(e, r[0], r[1], r[2], r[3]);
+            s_sts128(e + 16u, r[4], r[5], DIM > 6 ? r[DIM > 6 ? 6 : 0] : 0.f, DIM > 7 ? r[DIM > 7 ? 7 : 0] : 0.f);
+        }
+    }
+    static __device__ __forceinline__ void load(u32 e, float4 &f0, float4 &f1) {
+        f1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (DIM <= 4) {
+            f0 = s_lds128(e);
+        } else if constexpr (DIM <= 6) {
+            const float2 a = s_lds64(e), b = s_lds64(e + 8u), c = s_lds64(e + 16u);
+            f0 = make_float4(a.x, a.y, b.x, b.y);
+            f1 = make_float4(c.x, c.y, 0.f, 0.f);
+        } else {
+            f0 = s_lds128(e);
+            f1 = s_lds128(e + 16u);
+        }
+    }
+};
 
 __device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   // 16-byte aligned address, size a multiple of 16
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -110,7 +148,8 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   /
 template <int DIM, int WPC, int BPL>
 __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 tm /* shared address */, u32 cnt_s) {
     constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
-    constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per pending-list entry / per max-point record
+    constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per max-point record
+    constexpr u32 PE = PendEntry<DIM>::kBytes;     // bytes per pending-list entry
     constexpr u32 NW = WPC * BPL;                  // 32-bucket groups: flush-mask words, table slots per lane
     constexpr int G = 2;                           // 128-position chunks per block: 8 positions per lane in registers
     const u32 lane = lane_id();
@@ -122,7 +161,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     // team shared memory (32-bit shared addresses): pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} |
     // max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted per group) | part[2][S_MAXF][WPC] | fslot[WPC]
     const u32 pend = tm;
-    const u32 brec = tm + R * SP * PRB;
+    const u32 brec = tm + ((R * SP * PE + 15u) & ~15u);
     const u32 bmcs = brec + SP * 16;
     const u32 fmask = bmcs + SP * PRB;
     const u32 flist = fmask + ((NW + 3) & ~3u) * 4;
@@ -197,10 +236,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
             const bool hitmax = !(sqdist<DIM>(bmc[j], r) > S_OWNMAX(j));          // lowers the bucket's max point
             const bool want = ok && (touch || hitmax);
             if (want) {   // remember the sample: pend[np][bucket]
-                const u32 e = pend + (np[j] * SP + b) * PRB;
-                s_sts128(e, r[0], DIM > 1 ? r[DIM > 1 ? 1 : 0] : 0.f, DIM > 2 ? r[DIM > 2 ? 2 : 0] : 0.f, DIM > 3 ? r[DIM > 3 ? 3 : 0] : 0.f);
-                if constexpr (DIM > 4)
-                    s_sts128(e + 16u, r[4], DIM > 5 ? r[DIM > 5 ? 5 : 0] : 0.f, DIM > 6 ? r[DIM > 6 ? 6 : 0] : 0.f, DIM > 7 ? r[DIM > 7 ? 7 : 0] : 0.f);
+                PendEntry<DIM>::store(pend + (np[j] * SP + b) * PE, r);
                 ++np[j];
                 sts32(brec + b * 16 + 8, np[j]);
             }
@@ -298,14 +334,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
 #pragma unroll
                     for (int g = 0; g < G; ++g) v[g] = old[g];
                     // the next pending sample is fetched while the current one is applied
-                    const u32 e0 = pend + b * PRB, estep = SP * PRB;
-                    float4 n0 = s_lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if constexpr (DIM > 4) n1 = s_lds128(e0 + 16u);
+                    const u32 e0 = pend + b * PE, estep = SP * PE;
+                    float4 n0, n1;
+                    PendEntry<DIM>::load(e0, n0, n1);
                     for (u32 i = 0; i < nref; ++i) {
                         const float4 f0v = n0, f1v = n1;
-                        const u32 en = e0 + min(i + 1, nref - 1) * estep;
-                        n0 = s_lds128(en);
-                        if constexpr (DIM > 4) n1 = s_lds128(en + 16u);
+                        PendEntry<DIM>::load(e0 + min(i + 1, nref - 1) * estep, n0, n1);
                         const float w8[8] = {f0v.x, f0v.y, f0v.z, f0v.w, f1v.x, f1v.y, f1v.z, f1v.w};
                         u64 RC[DIM];   // the sample in both halves of a packed operand (FADD2 / FFMA2: two positions per instruction)
 #pragma unroll
@@ -509,7 +543,8 @@ static int stream_dim(int dim) { return dim <= 3 ? 3 : dim == 4 ? 4 : dim <= 6 ?
 
 static size_t stream_team_bytes(int dimp, u32 wpc, u32 bpl, u32 R) {
     const size_t SP = 32u * wpc * bpl, PRB = (size_t)((dimp + 3) / 4) * 16, NW = wpc * bpl;
-    size_t b = R * SP * PRB;
+    const size_t PE = dimp <= 4 ? 16 : dimp <= 6 ? 24 : 32;   // PendEntry<DIM>::kBytes
+    size_t b = (R * SP * PE + 15) & ~(size_t)15;
     b += SP * 16 + SP * PRB + ((NW + 3) & ~(size_t)3) * 4 + SP * 4;
     b += 2 * S_MAXF * wpc * S_REC + wpc * PRB;
     return (b + 15) & ~(size_t)15;
