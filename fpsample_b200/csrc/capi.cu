@@ -1,10 +1,12 @@
 // capi.cu -- the C-ABI layer (include/fps_b200.h): validation, device contexts, host<->device staging,
 // batch sharding over the devices of one box.  No torch / python types; no CPU fallback.
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -72,7 +74,7 @@ static const KnobDesc kKnobs[] = {
     {"WARP_TMEM", nullptr, &Tuning::warp_tmem}, {"WARP_LAZY", nullptr, &Tuning::warp_lazy},
     {"WARP_HYBRID", nullptr, &Tuning::warp_hybrid}, {"WARP_GLOBAL_MINB", &Tuning::warp_global_minb, nullptr},
     {"KDSMALL", nullptr, &Tuning::kdsmall},     {"STREAM_WARPS", nullptr, &Tuning::stream_warps},
-    {"PSUM", nullptr, &Tuning::psum},
+    {"PSUM", nullptr, &Tuning::psum},           {"STAGE", nullptr, &Tuning::stage},
     {"COUNT", nullptr, &Tuning::count},         {"PREFETCH", nullptr, &Tuning::prefetch},
 };
 static bool set_knob(const char *name, long v) {
@@ -149,8 +151,111 @@ struct Lane {  // one in-flight chunk: its own stream and buffers
     Buf in, out, ws, starts;
 };
 
+// ---- pageable host inputs: a few persistent host threads copy slices into page-locked slots and enqueue each slot's
+// transfer themselves ---------------------------------------------------------------------------------------------------
+// cudaMemcpyAsync from pageable memory goes through the driver's single bounce buffer at ~11 GB/s (measured on the B200
+// boxes: what a numpy user of the drop-in API gets).  Four threads memcpy at ~4 x one core's rate into their own pinned
+// slots, and the copy of the next slice overlaps the PCIe transfer of the previous one.  One pool per device context,
+// created at first use, never destroyed (its threads sleep on a condition variable between calls).
+struct StagePool {
+    static constexpr int T = 4, SLOTS = 2;
+    static constexpr size_t SLOT = (size_t)4 << 20;
+    struct Task {
+        const char *src;
+        char *dst;
+        size_t bytes;
+    };
+    struct Worker {
+        std::thread th;
+        void *slot[SLOTS] = {};
+        cudaEvent_t ev[SLOTS] = {};
+        cudaEvent_t done = nullptr;   // everything this worker enqueued so far (recorded by wait_all's caller)
+        cudaStream_t st = nullptr;
+        int next = 0;
+    };
+    int dev;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Task> q;
+    int pending = 0;
+    cudaError_t err = cudaSuccess;
+    Worker w[T];
+
+    explicit StagePool(int device) : dev(device) {   // (called with `device` current)
+        cudaError_t e = cudaSuccess;
+        for (int t = 0; t < T && e == cudaSuccess; ++t) {
+            e = cudaStreamCreateWithFlags(&w[t].st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w[t].done, cudaEventDisableTiming);
+            for (int i = 0; i < SLOTS && e == cudaSuccess; ++i) {
+                e = cudaMallocHost(&w[t].slot[i], SLOT);
+                if (e == cudaSuccess) e = cudaEventCreateWithFlags(&w[t].ev[i], cudaEventDisableTiming);
+            }
+        }
+        err = e;
+        for (int t = 0; t < T; ++t) w[t].th = std::thread([this, t] { run(t); });
+        for (int t = 0; t < T; ++t) w[t].th.detach();
+    }
+    void run(int t) {
+        Worker &me = w[t];
+        cudaError_t e = cudaSetDevice(dev);
+        for (;;) {
+            Task task;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+                cv_work.wait(lk, [this] { return !q.empty(); });
+                task = q.front();
+                q.pop_front();
+            }
+            if (e == cudaSuccess) {
+                const int i = me.next;
+                me.next = (i + 1) % SLOTS;
+                e = cudaEventSynchronize(me.ev[i]);   // the slot's previous transfer has left it
+                if (e == cudaSuccess) {
+                    memcpy(me.slot[i], task.src, task.bytes);
+                    e = cudaMemcpyAsync(task.dst, me.slot[i], task.bytes, cudaMemcpyHostToDevice, me.st);
+                }
+                if (e == cudaSuccess) e = cudaEventRecord(me.ev[i], me.st);
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    // every slice of [src, src + bytes) is copied and its transfer enqueued when this returns; `after` then waits for them
+    cudaError_t upload(void *dst, const void *src, size_t bytes, cudaStream_t after) {
+        {
+            // slices: all workers share a small piece (a quarter each, not below 256 KB), big ones go slot by slot
+            size_t step = (bytes + T - 1) / T;
+            step = (step + 4095) & ~(size_t)4095;
+            if (step < ((size_t)256 << 10)) step = (size_t)256 << 10;
+            if (step > SLOT) step = SLOT;
+            std::lock_guard<std::mutex> lk(mu);
+            for (size_t off = 0; off < bytes; off += step) {
+                q.push_back(Task{static_cast<const char *>(src) + off, static_cast<char *>(dst) + off, bytes - off < step ? bytes - off : step});
+                ++pending;
+            }
+        }
+        cv_work.notify_all();
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_done.wait(lk, [this] { return pending == 0; });
+            if (err != cudaSuccess) return err;
+        }
+        for (int t = 0; t < T; ++t) {
+            cudaError_t e = cudaEventRecord(w[t].done, w[t].st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(after, w[t].done, 0);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+};
+
 struct DevCtx {
     int dev = -1, n_sms = 0;
+    StagePool *stage = nullptr;
     std::mutex mu;
     Lane lane[2];
     Buf gout;                 // indices kept on the device for the NCCL gather (sharded entries)
@@ -631,6 +736,24 @@ struct ShardJob {
 // default: the legacy default stream, which orders behind every blocking stream of the caller
 static thread_local cudaStream_t tl_producer = cudaStreamLegacy;
 
+// Host -> device copy of one piece of the input, ordered before whatever is enqueued on `st` afterwards.  Page-locked sources
+// go straight to the copy engine; big pageable ones through the staging pool above.
+static int upload(DevCtx *cx, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    bool pageable = false;
+    if (bytes >= ((size_t)1 << 20) && tuning().stage != 0) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, src) == cudaSuccess) pageable = at.type == cudaMemoryTypeUnregistered;
+        else cudaGetLastError();
+    }
+    if (!pageable) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        return FPS_OK;
+    }
+    if (!cx->stage) cx->stage = new StagePool(cx->dev);
+    CK(cx->stage->upload(dst, src, bytes, st));
+    return FPS_OK;
+}
+
 static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
     const int dev = cx->dev;
     const Tuning &tu = tuning();
@@ -691,8 +814,7 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
             size_t c = 0;
             for (size_t b0 = 0; b0 < j.B; b0 += per, ++c) {
                 const size_t nb = (j.B - b0 < per) ? j.B - b0 : per;
-                CK(cudaMemcpyAsync(const_cast<float *>(d_in) + b0 * j.n * j.dim, j.pts + b0 * j.n * j.dim, nb * in_per,
-                                   cudaMemcpyHostToDevice, cp.st));
+                if ((rc = upload(cx, const_cast<float *>(d_in) + b0 * j.n * j.dim, j.pts + b0 * j.n * j.dim, nb * in_per, cp.st))) return rc;
                 CK(cudaEventRecord(cx->ev[c], cp.st));
                 CK(cudaStreamWaitEvent(ex.st, cx->ev[c], 0));
                 KdSmallPlan sp = L.sp;
@@ -760,7 +882,7 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
             CK(cudaMemcpyAsync(d_starts, j.start + b0 * j.n_starts, nb * j.n_starts * sizeof(u64),
                                cudaMemcpyHostToDevice, ln.st));
         }
-        if (!dev_in) CK(cudaMemcpyAsync(ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, cudaMemcpyHostToDevice, ln.st));
+        if (!dev_in && (rc = upload(cx, ln.in.p, j.pts + b0 * j.n * j.dim, nb * in_per, ln.st))) return rc;
         if (j.algo == FPS_ALGO_NPDU || j.algo == FPS_ALGO_NPDU_KNN) {
             cudaError_t e = j.algo == FPS_ALGO_NPDU
                                 ? launch_npdu(d_in, nb, j.n, j.dim, j.k, j.h /* window */, d_starts, d_res, ln.ws.p, cx->n_sms, ln.st)

@@ -187,6 +187,7 @@ struct Tuning {
     int stream_warps = -1;    // STREAM_WARPS: warps per cloud of the streaming sampler (1, 2, 4)
     int prefetch = -1;        // PREFETCH: 0 = the streaming sampler does not prefetch the buckets it is about to pass over into L2
     int psum = -1;            // PSUM: 0 = the grid-wide build never prepares the sequential sum's tiles in parallel (two-phase sum)
+    int stage = -1;           // STAGE: 0 = pageable host inputs use plain cudaMemcpyAsync instead of the threaded page-locked staging pool
     int count = -1;           // COUNT: 1 = the streaming sampler counts the work it executes (fps_b200_debug_counters)
 };
 const Tuning &tuning();

@@ -156,7 +156,7 @@ def test_alternative_samplers(knobs, oracle):
         elif big:
             shapes = [(30000, 3, 900, 7, 5, "u"), (20000, 6, 500, 6, 0, "u"), (40000, 2, 800, 5, 3, "g"), (50000, 1, 700, 5, 1, "g"),
                       (25000, 3, 600, 7, 2, "l"), (9000, 8, 300, 7, 4, "u"), (12345, 4, 1000, 7, 12344, "g"),
-                      (6001, 3, 6001, 7, 17, "g"), (4099, 5, 500, 3, 0, "u"), (70001, 3, 400, 9, 70000, "u")]
+                      (20001, 3, 20001, 7, 17, "g"), (30011, 5, 500, 3, 0, "u"), (70001, 3, 400, 9, 70000, "u")]
         else:
             shapes = [(4096, 3, 1024, 5, 0, "u"), (3000, 6, 500, 5, 7, "u"), (5000, 2, 700, 7, 1, "g"), (4096, 3, 600, 6, 9, "l")]
         for n, d, k, h, s, gen in shapes:
