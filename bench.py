@@ -495,6 +495,8 @@ def cfg5(wl, D, steps=2):
         FD.init_comm(D.rank, D.world)
     api = lambda: FD.bucket_fps_kdline_sampling_sharded(host, Btot, k, h, 0)
     allidx = api()
+    allidx = api()   # (two warm-ups: the result of the previous call is still alive when the next one starts, so rank 0's pool
+    #                   of page-locked result buffers needs two of them before it stops allocating)
     D.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
