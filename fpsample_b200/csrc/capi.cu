@@ -74,6 +74,7 @@ static const KnobDesc kKnobs[] = {
     {"WARP_TMEM", nullptr, &Tuning::warp_tmem}, {"WARP_LAZY", nullptr, &Tuning::warp_lazy},
     {"WARP_HYBRID", nullptr, &Tuning::warp_hybrid}, {"WARP_GLOBAL_MINB", &Tuning::warp_global_minb, nullptr},
     {"KDSMALL", nullptr, &Tuning::kdsmall},     {"STREAM_WARPS", nullptr, &Tuning::stream_warps},
+    {"STREAM_SPLIT", nullptr, &Tuning::stream_split},
     {"PSUM", nullptr, &Tuning::psum},           {"STAGE", nullptr, &Tuning::stage},
     {"COUNT", nullptr, &Tuning::count},         {"PREFETCH", nullptr, &Tuning::prefetch},
 };
@@ -630,8 +631,8 @@ static int enqueue_kdline(const float *d_pts, size_t B, size_t n, size_t dim, si
         tl_phase.mark(2, st);
         return FPS_OK;
     case Sampler::WarpStream:
-        set_plan("%s + kdline_stream_kernel<DIM=%d,WPC=%u,BPL=%u> (points in HBM, %u warp%s per cloud) R=%u clouds=%zu grid=%u smem=%zu",
-                 bdesc, L.stp.dimp, L.stp.wpc, L.stp.bpl, L.stp.wpc, L.stp.wpc > 1 ? "s" : "", L.stp.rs, B, L.stp.grid, L.stp.smem);
+        set_plan("%s + kdline_stream_kernel<DIM=%d> (points in HBM, a team of warps per cloud): %s; clouds=%zu", bdesc, L.stp.dimp,
+                 L.stp.desc, B);
         tl_phase.mark(0, st);
         if (int rcb = build_regions()) return rcb;
         tl_phase.mark(1, st);
@@ -786,7 +787,16 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
         if (nch > 8) nch = 8;
         if (dev_in) nch = 1;
     }
-    const size_t chunk = (j.B + nch - 1) / nch;
+    size_t chunk = (j.B + nch - 1) / nch;
+    if (nch > 1 && j.algo == FPS_ALGO_KDLINE) {
+        // the streaming sampler works in waves of 8 two-warp teams per SM (kdline_stream.cu: plan_kdline_stream): chunks of
+        // whole waves, so that only the last chunk of the batch has a partial wave (which then runs on 4-warp teams)
+        KdLayout L;
+        if (kd_layout(chunk, j.n, j.dim, j.h, cx->n_sms, false, &L) == cudaSuccess && L.sampler == Sampler::WarpStream) {
+            const size_t wave = (size_t)8 * cx->n_sms;
+            chunk = (chunk + wave - 1) / wave * wave;
+        }
+    }
     static_assert(sizeof(size_t) == sizeof(u64), "size_t must be 64-bit");
     int rc = FPS_OK;
     // One batch of small clouds (the on-chip sampler wants all of them in one launch): the upload is cut into pieces and

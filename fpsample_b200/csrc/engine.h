@@ -115,10 +115,15 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
                                u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, cudaStream_t st);
 
 // ---- kd-line, a team of 1 / 2 / 4 warps per cloud over prebuilt regions left in global memory (kdline_stream.cu) --------
-struct StreamPlan {
-    int dimp;
-    u32 wpc /* warps per cloud */, bpl /* buckets per lane */, rs /* pending samples per bucket */, team_bytes, grid;
+struct StreamSeg {   // one launch: `clouds` consecutive clouds of the batch on teams of `wpc` warps
+    u32 wpc /* warps per cloud */, bpl /* buckets per lane */, rs /* pending samples per bucket */, team_bytes, grid, clouds;
     size_t smem;
+};
+struct StreamPlan {   // a batch is cut into at most three runs of clouds, narrow teams first (kdline_stream.cu: plan_kdline_stream)
+    int dimp;
+    u32 nseg;
+    StreamSeg seg[3];
+    char desc[160];   // "1184 clouds x 2 warps (R=11) + 16 clouds x 4 warps (R=16)"
 };
 bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl);
 cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
@@ -185,6 +190,7 @@ struct Tuning {
     long warp_global_minb = -1;   // WARP_GLOBAL_MINB: smallest batch the streaming sampler takes
     int kdsmall = -1;         // KDSMALL: 0 forbids the shared-memory build kernel
     int stream_warps = -1;    // STREAM_WARPS: warps per cloud of the streaming sampler (1, 2, 4)
+    int stream_split = -1;    // STREAM_SPLIT: 0 = one team size per batch; 1 (default) = full waves of narrow teams + a tail of wide ones; 2 = also one-warp teams
     int prefetch = -1;        // PREFETCH: 0 = the streaming sampler does not prefetch the buckets it is about to pass over into L2
     int psum = -1;            // PSUM: 0 = the grid-wide build never prepares the sequential sum's tiles in parallel (two-phase sum)
     int stage = -1;           // STAGE: 0 = pageable host inputs use plain cudaMemcpyAsync instead of the threaded page-locked staging pool

@@ -28,15 +28,21 @@
 // cp.async.bulk.prefetch per component the moment its owner lane decides so, before the first barrier.
 #include <cfloat>
 
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
 #include "common.cuh"
 #include "engine.h"
 
 namespace fps {
 
 constexpr u32 S_NONE = 0xffffffffu;
-constexpr int S_U = 8;              // chunks (of 32 positions) per block of a bucket pass
 constexpr u32 S_MAXF = 4;           // flushed buckets per exchange batch (1.3 - 2.2 per pick on the BASELINE clouds)
-constexpr u32 S_THREADS = 512;      // 16 warps per CTA, one CTA per SM (128 registers per thread)
+#ifndef S_THREADS_DEF
+#define S_THREADS_DEF 512
+#endif
+constexpr u32 S_THREADS = S_THREADS_DEF;   // 16 warps per CTA, one CTA per SM (128 registers per thread)
 constexpr u32 S_REC = 48;           // bytes of a partial record: max bits, position, up to 8 coordinates
 constexpr u32 S_MAXR = 16;          // pending samples per bucket at most
 
@@ -158,15 +164,18 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     const float *q = reinterpret_cast<const float *>(rg);
     float *dis = reinterpret_cast<float *>(rg) + (size_t)dim * npad;
 
-    // team shared memory (32-bit shared addresses): pending lists [R][SP] | bucket records [SP] {lo, hi, pending, -} |
-    // max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted per group) | part[2][S_MAXF][WPC] | fslot[WPC]
-    const u32 pend = tm;
-    const u32 brec = tm + ((R * SP * PE + 15u) & ~15u);
+    // team shared memory (32-bit shared addresses).  Everything whose size is known at compile time comes FIRST, so that its
+    // address is `tm` + an immediate (no address arithmetic, no registers); the pending lists, whose depth R is a run-time
+    // choice of the planner, come last:
+    // bucket records [SP] {lo, hi, pending, -} | max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted
+    // per group) | part[2][S_MAXF][WPC] | fslot[WPC] | pending lists [R][SP]
+    const u32 brec = tm;
     const u32 bmcs = brec + SP * 16;
     const u32 fmask = bmcs + SP * PRB;
     const u32 flist = fmask + ((NW + 3) & ~3u) * 4;
     const u32 part = flist + SP * 4;
     const u32 fslot = part + 2 * S_MAXF * WPC * S_REC + tw * PRB;   // one per warp
+    const u32 pend = part + 2 * S_MAXF * WPC * S_REC + WPC * PRB;
 
     // ---- distances start at FLT_MAX (Point.h:61-65); bucket boundaries to shared memory ------------------------------
     for (u32 p = (tw * 32 + lane) * 4; p < npad; p += WPC * 128)
@@ -550,43 +559,94 @@ static size_t stream_team_bytes(int dimp, u32 wpc, u32 bpl, u32 R) {
     return (b + 15) & ~(size_t)15;
 }
 
+// one team size: buckets per lane, pending-list depth and shared memory of a CTA of S_THREADS / 32 / wpc teams
+static bool stream_seg(int dimp, u32 S, u32 wpc, size_t clouds, int n_sms, StreamSeg *sg) {
+    const size_t cap = 227 * 1024 - 256;
+    const u32 bpl = wpc == 1 ? 4 : wpc == 2 ? 2 : (S <= 128 ? 1 : S <= 256 ? 2 : 4);
+    if (32u * wpc * bpl < S) return false;
+    const u32 teams = S_THREADS / 32 / wpc;
+    u32 R = S_MAXR;
+    while (R > 3 && teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) --R;
+    if (teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) return false;
+    sg->wpc = wpc;
+    sg->bpl = bpl;
+    sg->rs = R;
+    sg->team_bytes = (u32)stream_team_bytes(dimp, wpc, bpl, R);
+    sg->smem = (size_t)teams * sg->team_bytes;
+    sg->clouds = (u32)clouds;
+    sg->grid = (u32)(clouds < (size_t)n_sms ? clouds : (size_t)n_sms);   // spread over every SM before stacking teams
+    return true;
+}
+
 bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl) {
     if (dim == 0 || dim > 8 || h == 0 || h > 9 || n == 0 || B == 0) return false;
     const Tuning &tu = tuning();
     const u32 S = 1u << h;
     const int dimp = stream_dim((int)dim);
-    const size_t cap = 227 * 1024 - 256;
-    // warps per cloud (measured, 100 k-point clouds x 3, 2^7 buckets, one B200): a pick is a dependent chain and an SM only
-    // overlaps as many chains as it has teams, so big batches want many small teams and small shards want the chain itself
-    // short.  Sampling ms for 1 / 2 / 4 warps per cloud: 4096 clouds 171 / 175 / 214, 2048: 86 / 88 / 117, 1024: 85 / 44 / 60,
-    // 512: 94 / 56 / 28.  One-warp teams only have room for 4 pending samples per bucket (0.23 early passes per pick, +18 % DRAM
-    // traffic) and buy nothing over two: they stay a knob.  Records of more than 4 dimensions need the shared memory of a
-    // 4-warp team for useful pending lists.
-    const size_t slots = (size_t)(S_THREADS / 32) * n_sms;   // one-warp teams the GPU holds (2368)
-    u32 wpc = dimp > 4 ? 4 : (B >= slots / 3 ? 2 : 4);
-    if (tu.stream_warps == 1 || tu.stream_warps == 2 || tu.stream_warps == 4) wpc = (u32)tu.stream_warps;
-    if (S > 128) wpc = 4;
-    u32 bpl = 0, teams = 0, R = 0;
-    for (;; wpc *= 2) {   // a team too small for its shared memory (wide records): the next size up
-        bpl = wpc == 1 ? 4 : wpc == 2 ? 2 : (S <= 128 ? 1 : S <= 256 ? 2 : 4);
-        teams = S_THREADS / 32 / wpc;
-        R = S_MAXR;
-        while (R > 3 && teams * stream_team_bytes(dimp, wpc, bpl, R) > cap) --R;
-        if (teams * stream_team_bytes(dimp, wpc, bpl, R) <= cap) break;
-        if (wpc == 4) return false;
+    // Warps per cloud (measured, 100 k-point clouds x 3, 2^7 buckets, one B200).  A pick is a dependent chain whose length hardly
+    // depends on how many other teams share the SM: a cloud takes ~85 / 44 / 28 ms on a team of 1 / 2 / 4 warps whether the SM
+    // is full or not, and an SM holds 16 / 8 / 4 such teams.  So a batch wants FULL WAVES of narrow teams (most clouds per SM)
+    // and a last, partial wave of wide teams (short chain) instead of a half-empty wave of narrow ones: 4096 clouds =
+    // 3 x 1184 on two warps + 544 on four, not 3.46 waves of two-warp teams.  The cut is a small dynamic programme over the
+    // remaining clouds in units of one wave of the widest team.  One-warp teams only have room for 4 pending samples per
+    // bucket (+18 % DRAM traffic) and are opt-in (STREAM_SPLIT=2); records of more than 4 dimensions and more than 128
+    // buckets need the shared memory / lanes of a 4-warp team.
+    const u32 widths[3] = {1, 2, 4};
+    const double cost[3] = {85.0, 44.0, 28.0};
+    StreamSeg cand[3];
+    bool ok[3];
+    for (int i = 0; i < 3; ++i) ok[i] = stream_seg(dimp, S, widths[i], 1, n_sms, &cand[i]);
+    if (!ok[2]) return false;
+    const int split = tu.stream_split < 0 ? 1 : tu.stream_split;
+    if (dimp > 4 || S > 128) ok[0] = ok[1] = false;
+    if (split < 2) ok[0] = false;
+    size_t take[3] = {0, 0, 0};   // clouds per team size
+    if (tu.stream_warps == 1 || tu.stream_warps == 2 || tu.stream_warps == 4) {
+        int i = tu.stream_warps == 1 ? 0 : tu.stream_warps == 2 ? 1 : 2;
+        while (!stream_seg(dimp, S, widths[i], 1, n_sms, &cand[i])) ++i;   // a team too small for its shared memory: the next size up
+        take[i] = B;
+    } else if (split == 0) {
+        const size_t slots = (size_t)(S_THREADS / 32) * n_sms;   // one-warp teams the GPU holds (2368)
+        take[(ok[1] && B >= slots / 3) ? 1 : 2] = B;
+    } else {
+        const size_t unit = (size_t)(S_THREADS / 32 / 4) * n_sms;   // one wave of 4-warp teams (592)
+        const size_t J = (B + unit - 1) / unit;
+        std::vector<double> best(J + 1, 0.0);
+        std::vector<int> pick(J + 1, 2);
+        for (size_t j = 1; j <= J; ++j) {   // j units still to place
+            best[j] = 1e300;
+            for (int i = 0; i < 3; ++i) {
+                if (!ok[i]) continue;
+                const size_t wave = 4 / widths[i];   // units one wave of this team size takes
+                const double c = cost[i] + (j > wave ? best[j - wave] : 0.0);
+                if (c < best[j] - 1e-9) best[j] = c, pick[j] = i;
+            }
+        }
+        size_t left = B;
+        for (size_t j = J; j > 0 && left > 0;) {
+            const int i = pick[j];
+            const size_t wave = 4 / widths[i], cl = wave * unit < left ? wave * unit : left;
+            take[i] += cl;
+            left -= cl;
+            j = j > wave ? j - wave : 0;
+        }
     }
     pl->dimp = dimp;
-    pl->wpc = wpc;
-    pl->bpl = bpl;
-    pl->rs = R;
-    pl->team_bytes = (u32)stream_team_bytes(dimp, wpc, bpl, R);
-    pl->smem = (size_t)teams * pl->team_bytes;
-    pl->grid = (u32)(B < (size_t)n_sms ? B : (size_t)n_sms);   // spread over every SM before stacking teams
-    return true;
+    pl->nseg = 0;
+    pl->desc[0] = 0;
+    for (int i = 0; i < 3; ++i) {   // narrow teams first: the wide ones finish the batch
+        if (!take[i]) continue;
+        StreamSeg &sg = pl->seg[pl->nseg++];
+        if (!stream_seg(dimp, S, widths[i], take[i], n_sms, &sg)) return false;
+        const size_t len = strlen(pl->desc);
+        snprintf(pl->desc + len, sizeof(pl->desc) - len, "%s%u clouds x WPC=%u (BPL=%u R=%u grid=%u smem=%zu)", len ? " + " : "", sg.clouds,
+                 sg.wpc, sg.bpl, sg.rs, sg.grid, sg.smem);
+    }
+    return pl->nseg > 0;
 }
 
 template <int DIM, int WPC, int BPL>
-static cudaError_t launch_stream_t(const StreamPlan &pl, const StreamArgs &a, cudaStream_t st) {
+static cudaError_t launch_stream_t(const StreamSeg &pl, const StreamArgs &a, cudaStream_t st) {
     auto kern = kdline_stream_kernel<DIM, WPC, BPL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
@@ -595,7 +655,7 @@ static cudaError_t launch_stream_t(const StreamPlan &pl, const StreamArgs &a, cu
 }
 
 template <int DIM>
-static cudaError_t launch_stream_d(const StreamPlan &pl, const StreamArgs &a, cudaStream_t st) {
+static cudaError_t launch_stream_d(const StreamSeg &pl, const StreamArgs &a, cudaStream_t st) {
     if (pl.wpc == 1) return launch_stream_t<DIM, 1, 4>(pl, a, st);
     if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2>(pl, a, st);
     if (pl.bpl == 1) return launch_stream_t<DIM, 4, 1>(pl, a, st);
@@ -608,38 +668,44 @@ cudaError_t stream_debug_counters(u64 *out16) { return cudaMemcpyFromSymbol(out1
 cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,
                                  u32 *counter, u32 B, u32 n, u32 dim, u32 k, u32 h, bool count, cudaStream_t st) {
     StreamArgs a;
-    a.region = region;
     a.region_stride = region_stride;
-    a.starts = starts;
-    a.out = out;
-    a.counter = counter;
-    a.B = B;
     a.n = n;
     a.npad = (n + 31) & ~31u;
     a.dim = dim;
     a.k = k;
     a.S = 1u << h;
     a.nlo_pad = (a.S + 1 + 31) & ~31u;
-    a.R = pl.rs;
-    a.team_bytes = pl.team_bytes;
     a.count = count ? 1u : 0u;
     a.prefetch = tuning().prefetch != 0 ? 1u : 0u;
     a.negzero = 0x8000000080000000ull;
-    cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
+    cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);   // one hand-out counter per launch, 64 bytes apart
     if (e != cudaSuccess) return e;
     if (count) {
         void *sym = nullptr;
         if ((e = cudaGetSymbolAddress(&sym, g_stream_wexec)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(sym, 0, sizeof(u64) * 16, st)) != cudaSuccess) return e;
     }
-    switch (pl.dimp) {
-        case 3: e = launch_stream_d<3>(pl, a, st); break;
-        case 4: e = launch_stream_d<4>(pl, a, st); break;
-        case 6: e = launch_stream_d<6>(pl, a, st); break;
-        default: e = launch_stream_d<8>(pl, a, st); break;
+    size_t b0 = 0;
+    for (u32 i = 0; i < pl.nseg; ++i) {
+        const StreamSeg &sg = pl.seg[i];
+        a.region = region + b0 * region_stride;
+        a.starts = starts ? starts + b0 : nullptr;
+        a.out = out + b0 * (size_t)k;
+        a.counter = counter + 16 * i;
+        a.B = sg.clouds;
+        a.R = sg.rs;
+        a.team_bytes = sg.team_bytes;
+        switch (pl.dimp) {
+            case 3: e = launch_stream_d<3>(sg, a, st); break;
+            case 4: e = launch_stream_d<4>(sg, a, st); break;
+            case 6: e = launch_stream_d<6>(sg, a, st); break;
+            default: e = launch_stream_d<8>(sg, a, st); break;
+        }
+        count_launch();
+        if (e != cudaSuccess) return e;
+        b0 += sg.clouds;
     }
-    count_launch();
-    return e;
+    return b0 == B ? cudaSuccess : cudaErrorInvalidValue;
 }
 
 }  // namespace fps

@@ -191,7 +191,7 @@ FPS_API const char *fps_b200_last_plan(void);       /* thread-local: which kerne
 FPS_API int fps_b200_debug_counters(int which, uint64_t *out16);
 /* Planner overrides (tests, experiments).  The library reads FPS_B200_<NAME> from the environment ONCE, at first use; after
  * that only this call changes a knob.  value -1 = the planner's own choice.  Names: GRID, GROUP, GRIDBUILD, VANILLA_KD, PIPE,
- * ZEROCOPY, GRID_ECAP, WARP, WARP_TMEM, WARP_LAZY, WARP_HYBRID, WARP_GLOBAL_MINB, KDSMALL, STREAM_WARPS, COUNT, PREFETCH, PSUM, STAGE. */
+ * ZEROCOPY, GRID_ECAP, WARP, WARP_TMEM, WARP_LAZY, WARP_HYBRID, WARP_GLOBAL_MINB, KDSMALL, STREAM_WARPS, STREAM_SPLIT, COUNT, PREFETCH, PSUM, STAGE. */
 FPS_API int fps_b200_set_tuning(const char *name, long value);
 /* Device-resident inputs of the host-pointer entries: the calling thread's NEXT call waits (on the device, through an event)
  * for the work queued on `stream` -- the stream that produced the points -- instead of the legacy default stream.  Nothing is

@@ -1,6 +1,6 @@
 """cfg5-shaped batches (100k points -> 8192, h=7): the streaming sampler with 1 / 2 / 4 warps per cloud at the per-GPU batch
 sizes of a 1..8-GPU split; build / sampling split, executed-work counters, a few clouds checked against the oracle.
-usage: python scripts/cmp_cfg5.py D B [B ...] [--wpc 1,2,4] [--check N]"""
+usage: python scripts/cmp_cfg5.py D B [B ...] [--wpc=1,2,4] [--check=N] [--split=0|1|2]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -13,6 +13,7 @@ Bs = [int(x) for x in args[1:]] or [512]
 wpcs = [int(x) for x in opt.get("wpc", "-1").split(",")]
 ncheck = int(opt.get("check", "2"))
 if "prefetch" in opt: capi.set_tuning("PREFETCH", int(opt["prefetch"]))
+if "split" in opt: capi.set_tuning("STREAM_SPLIT", int(opt["split"]))
 nreal = 32
 base = np.stack([synth.uniform(3000 + b, n, d) for b in range(nreal)])
 want = {b: O.kdline(base[b], k, h, 0) for b in range(ncheck)}
@@ -35,9 +36,10 @@ for B in Bs:
         capi.set_tuning("COUNT", -1)
         got = do.cpu().numpy().astype(np.uint64)
         ok = all(np.array_equal(got[b + nreal * j], want[b]) for b in want for j in range((B - b + nreal - 1) // nreal) if b + nreal * j < B)
+        ok = ok and all(np.array_equal(got[b], got[b % nreal]) for b in range(nreal, B))   # every copy of a cloud, whatever team took it
         pts, pu, fl, early, tests, picks, clouds, stored = [int(x) for x in cnt[:8]]
         byt = pts * 4 * (d + 1) + stored * 4
         print(f"B={B} d={d} wpc={wpc}: build {best[0]:7.2f} ms sampling {best[1]:7.2f} ms -> {B / sum(best) * 1e3:7.0f} clouds/s | parity {'OK' if ok else 'MISMATCH'} | "
               f"per pick: {pts / max(picks, 1):.0f} pts scanned, {pu / max(picks, 1):.0f} point-updates, {fl / max(picks, 1):.2f} passes ({early / max(picks, 1):.2f} early) | "
-              f"{byt / 1e9:.1f} GB algorithmic -> {byt / best[1] / 1e6:.0f} GB/s | {capi.last_plan().split(' + ')[-1][:110]}", flush=True)
+              f"{byt / 1e9:.1f} GB algorithmic -> {byt / best[1] / 1e6:.0f} GB/s | {capi.last_plan().split('): ')[-1][:150]}", flush=True)
         del ws

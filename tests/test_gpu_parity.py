@@ -570,7 +570,9 @@ def test_cfg5_production_plan(d, B, ncheck, oracle):
     pcs = synth.uniform_batch(3000, B, n, d)
     got = capi.kdline_batch(pcs, k, h, devices=[0])
     plan = capi.last_plan()
-    assert "kdline_stream_kernel" in plan and ("WPC=2" if d == 3 else "WPC=4") in plan and "gb_* grid-wide build" in plan, plan
+    # 1200 clouds of 3-D points = one full wave of two-warp teams (8 per SM) + a tail on four-warp teams; 6-D records: four warps
+    assert "kdline_stream_kernel" in plan and "gb_* grid-wide build" in plan and "WPC=4" in plan, plan
+    assert ("1184 clouds x WPC=2" in plan and "16 clouds x WPC=4" in plan) if d == 3 else "WPC=2" not in plan, plan
     for b in range(B):
         assert got[b].max() < n
     for b in range(0, B, 7):
@@ -588,6 +590,10 @@ def test_cfg5_production_plan(d, B, ncheck, oracle):
             one = capi.kdline_batch(pcs[:400], k, h, devices=[0])
             assert "WPC=1" in capi.last_plan(), capi.last_plan()
         np.testing.assert_array_equal(one, got[:400])
+        with capi.tuning(stream_split=0):   # one team size for the whole batch (the planner before the wave split)
+            two = capi.kdline_batch(pcs[600:], k, h, devices=[0])
+            assert "600 clouds x WPC=4" in capi.last_plan(), capi.last_plan()
+        np.testing.assert_array_equal(two, got[600:])
 
 
 def test_executed_work_counters_of_the_streaming_sampler(oracle):
