@@ -45,7 +45,6 @@ struct WarpArgs {
     u32 B, n, npad, dim, k, S, nlo_pad;
     u32 nch;            // chunks per cloud, padded to a multiple of W_U
     u32 n_tmem_warps, n_smem_warps, slot_bytes, meta_bytes, R, lazy, hybrid;
-    u64 negzero;        // two binary32 -0.0 as an operand the compiler cannot see through (packed products, common.cuh)
 };
 
 __device__ __forceinline__ float4 lds128(u32 a) {
@@ -69,13 +68,13 @@ __device__ __forceinline__ void sts64(u32 a, float x, float y) {
 // ---- the two point stores ---------------------------------------------------------------------------------------
 // component c (0..DIM-1 coordinates, DIM = running distance) of position (chunk, lane)
 struct SmemStore {
-    static constexpr bool kTrackCoords = false, kCoordsInPlace = false, kWide = false;
+    static constexpr bool kTrackCoords = false;
     u32 base;   // shared-space byte address of this warp's slot
     u32 lst;    // words per (component, lane) row: nch + 4 (16-byte aligned rows, conflict-free 128-bit access)
     __device__ __forceinline__ u32 addr(u32 comp, u32 lane, u32 chunk) const { return base + ((comp * 32u + lane) * lst + chunk) * 4u; }
     // U consecutive chunks: 8 start at a multiple of 4 (two 128-bit accesses), 4 and 6 at an even chunk (64-bit accesses)
     template <int U>
-    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
+    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U]) const {
         const u32 a = addr(comp, lane, cb);
         if constexpr (U == 8) {
             const float4 f0 = lds128(a), f1 = lds128(a + 16u);
@@ -112,7 +111,7 @@ struct SmemStore {
 struct TmemStore {
     // a point lookup is three tcgen05.ld + a wait + three shuffles on the pick path: lanes remember their candidate's
     // coordinates instead (three selects per chunk of a bucket pass) and the winner broadcasts them
-    static constexpr bool kTrackCoords = true, kCoordsInPlace = false, kWide = false;
+    static constexpr bool kTrackCoords = true;
     u32 base;   // tensor-memory address of this warp's lane quarter: (32 * (warp % 4)) << 16 | first column
     u32 nch;    // columns per component
     __device__ __forceinline__ void ld4(u32 col, u32 *w) const {
@@ -124,7 +123,7 @@ struct TmemStore {
                      : "memory");
     }
     template <int U>
-    __device__ __forceinline__ void load(u32 comp, u32, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
+    __device__ __forceinline__ void load(u32 comp, u32, u32 cb, float (&v)[U]) const {
         u32 w[U];
         const u32 col = base + comp * nch + cb;
         if constexpr (U == 8) {
@@ -175,12 +174,12 @@ struct TmemStore {
 // (BASELINE.json cfg 3) is 192 KB of coordinates + 64 KB of distances -- more than either store alone, exactly what one
 // SM has when both are used.  One such warp per SM (its distances fill one lane quarter of TMEM).
 struct HybridStore {
-    static constexpr bool kTrackCoords = false, kCoordsInPlace = false, kWide = false;
+    static constexpr bool kTrackCoords = false;
     SmemStore s;   // DIM components
     TmemStore t;   // one component: the distance of chunk c is column c
     u32 dimc;      // index of the distance component (= DIM of the kernel)
     template <int U>
-    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U], u32 = 0, bool = false) const {
+    __device__ __forceinline__ void load(u32 comp, u32 lane, u32 cb, float (&v)[U]) const {
         if (comp == dimc) t.load<U>(0, lane, cb, v);
         else s.load<U>(comp, lane, cb, v);
     }
@@ -227,7 +226,7 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
     // ---- stage the permuted cloud into this warp's store; distances start at FLT_MAX (Point.h:61-65) ---------
     for (u32 cb = 0; cb < nch; cb += W_U) {
 #pragma unroll
-        for (int c = ST::kCoordsInPlace ? DIM : 0; c <= DIM; ++c) {   // a global store holds the coordinates already
+        for (int c = 0; c <= DIM; ++c) {
             float v[W_U];
 #pragma unroll
             for (int u = 0; u < W_U; ++u) {
@@ -330,8 +329,8 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 constexpr int U = decltype(Uc)::value;
                 float x[DIM][U], v[U], old[U];
 #pragma unroll
-                for (int c = 0; c < DIM; ++c) st.template load<U>(c, lane, cb, x[c], dim, false);
-                st.template load<U>(DIM, lane, cb, old, dim, true);
+                for (int c = 0; c < DIM; ++c) st.template load<U>(c, lane, cb, x[c]);
+                st.template load<U>(DIM, lane, cb, old);
                 st.wait_ld();
 #pragma unroll
                 for (int u = 0; u < U; ++u) v[u] = old[u];
@@ -343,40 +342,23 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 float4 n0 = lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if constexpr (DIM > 4) n1 = lds128(e0 + 16u);
                 for (u32 i = 0; i < nref; ++i) {
-                    const float4 f0 = n0, f1 = n1;
+                    const float4 f0 = n0;
+                    [[maybe_unused]] const float4 f1 = n1;
                     const u32 en = e0 + min(i + 1, nref - 1) * estep;
                     n0 = lds128(en);
                     if constexpr (DIM > 4) n1 = lds128(en + 16u);
                     float w[8];
                     w[0] = f0.x, w[1] = f0.y, w[2] = f0.z, w[3] = f0.w;
                     if constexpr (DIM > 4) w[4] = f1.x, w[5] = f1.y, w[6] = f1.z, w[7] = f1.w;
-                    if constexpr (ST::kCoordsInPlace) {
-                        // global store (8 warps per SM, registers to spare): two chunks per FADD2 / FFMA2 (U is even);
-                        // on the on-chip stores the packed form costs the registers the 7-warp CTA does not have
-                        u64 RC[DIM];   // the sample, broadcast into both halves of a packed operand
+                    float ref[DIM];
 #pragma unroll
-                        for (int c = 0; c < DIM; ++c) RC[c] = pk2(w[c], w[c]);
+                    for (int c = 0; c < DIM; ++c) ref[c] = w[c];
 #pragma unroll
-                        for (int u = 0; u < U; u += 2) {
-                            u64 PT[DIM];
+                    for (int u = 0; u < U; ++u) {
+                        float pt[DIM];
 #pragma unroll
-                            for (int c = 0; c < DIM; ++c) PT[c] = pk2(x[c][u], x[c][u + 1]);
-                            float d0, d1;
-                            up2(sqdist2<DIM>(PT, RC, a.negzero), d0, d1);
-                            v[u] = fminf(v[u], d0);   // std::min(dis, d), Point.h:82-86
-                            v[u + 1] = fminf(v[u + 1], d1);
-                        }
-                    } else {
-                        float ref[DIM];
-#pragma unroll
-                        for (int c = 0; c < DIM; ++c) ref[c] = w[c];
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            float pt[DIM];
-#pragma unroll
-                            for (int c = 0; c < DIM; ++c) pt[c] = x[c][u];
-                            v[u] = fminf(v[u], sqdist<DIM>(pt, ref));   // std::min(dis, d), Point.h:82-86
-                        }
+                        for (int c = 0; c < DIM; ++c) pt[c] = x[c][u];
+                        v[u] = fminf(v[u], sqdist<DIM>(pt, ref));   // std::min(dis, d), Point.h:82-86
                     }
                 }
                 // positions outside [lo, hi) belong to a neighbour bucket (or are padding): they keep their value
@@ -405,15 +387,11 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 block(std::integral_constant<int, 6>{}, min(c0, nch - 6u));
             } else {
                 u32 cb0 = c0 & ~3u;
-                if constexpr (ST::kWide) {
-                    // points in global memory: a block's loads are one L2 / HBM round trip, so the big buckets of big clouds
-                    // go in blocks of 16 chunks (twice the bytes in flight per warp, half the round trips per bucket pass)
-                    if (nch >= 16)
-                        for (; cb0 + 8 <= c1b; cb0 += 16) block(std::integral_constant<int, 16>{}, min(cb0, nch - 16u));
-                }
                 for (; cb0 <= c1b; cb0 += W_U) block(std::integral_constant<int, W_U>{}, min(cb0, nch - W_U));
             }
-            st.wait_st();   // a neighbouring bucket may share this bucket's first / last chunk
+            // a neighbouring bucket may share this bucket's first / last chunk.  (Waiting here, right behind the stores, is
+            // faster than waiting in front of the next pass's loads: 1.23 against 1.31 ms on BASELINE cfg 2.)
+            st.wait_st();
             // bucket max, then its lowest position; the owner lane takes both plus the point's coordinates
             const float pv = fmaxf(best, 0.0f);
             const u32 m = __reduce_max_sync(FULL, __float_as_uint(pv));
@@ -664,7 +642,6 @@ cudaError_t launch_kdline_warp(const WarpPlan &pl, unsigned char *region, size_t
     a.R = pl.rs;
     a.lazy = pl.lazy;
     a.hybrid = pl.hybrid;
-    a.negzero = 0x8000000080000000ull;
     cudaError_t e = cudaMemsetAsync(counter, 0, 256, st);
     if (e != cudaSuccess) return e;
     const bool b1 = pl.bpl == 1;
