@@ -43,6 +43,7 @@ EXPORTS = {
     "fps_b200_comm_destroy": (None, []),
     "fps_b200_comm_ranks": (ctypes.c_int, []),
     "fps_b200_nccl_version": (ctypes.c_int, []),
+    "fps_b200_nccl_library": (ctypes.c_int, [ctypes.c_char_p]),
     "fps_b200_kdline_batch_sharded": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "fps_b200_vanilla_batch_sharded": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 4 + [ctypes.c_void_p, ctypes.c_void_p]),
     "fps_b200_gather_indices": (ctypes.c_int, [ctypes.c_void_p] + [ctypes.c_size_t] * 3 + [ctypes.c_void_p]),
@@ -70,7 +71,24 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         _lib = L
+        p = _bundled_nccl()
+        if p:   # the copy PyTorch would load if it is imported after the first comm call (include/fps_b200.h)
+            L.fps_b200_nccl_library(p.encode())
     return _lib
+
+
+def _bundled_nccl():
+    """Path of the pip-installed nvidia-nccl wheel's libnccl.so.2, if there is one (nothing is imported)."""
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        return None
+    for d in (spec.submodule_search_locations or []) if spec else []:
+        p = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(p):
+            return p
+    return None
 
 
 class FpsError(RuntimeError):

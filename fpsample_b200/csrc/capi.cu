@@ -805,7 +805,8 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
     if (!dev_in && j.algo == FPS_ALGO_KDLINE && nch == 1 && j.B >= 64 && j.B * in_per >= ((size_t)4 << 20) && tu.pipe != 0) {
         KdLayout L;
         CK(kd_layout(j.B, j.n, j.dim, j.h, cx->n_sms, false, &L));
-        if ((L.sampler == Sampler::WarpOnChip || L.sampler == Sampler::WarpStream) && L.builder == Builder::Small) {
+        if ((L.sampler == Sampler::WarpOnChip || L.sampler == Sampler::WarpStream) &&
+            (L.builder == Builder::Small || L.builder == Builder::GridWide)) {
             Lane &cp = cx->lane[0], &ex = cx->lane[1];
             if ((rc = cp.in.ensure(j.B * in_per)) || (rc = cp.out.ensure(j.B * out_per)) || (rc = cp.ws.ensure(L.total))) return rc;
             u64 *d_starts = nullptr;
@@ -827,11 +828,16 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
                 if ((rc = upload(cx, const_cast<float *>(d_in) + b0 * j.n * j.dim, j.pts + b0 * j.n * j.dim, nb * in_per, cp.st))) return rc;
                 CK(cudaEventRecord(cx->ev[c], cp.st));
                 CK(cudaStreamWaitEvent(ex.st, cx->ev[c], 0));
-                KdSmallPlan sp = L.sp;
-                const size_t gmax = (size_t)sp.occ * (size_t)cx->n_sms;
-                sp.grid = (u32)(nb < gmax ? nb : gmax);
-                CK(launch_kdsmall(sp, d_in + b0 * j.n * j.dim, region + b0 * L.region_stride, L.region_stride,
-                                  reinterpret_cast<u32 *>(ws), (u32)nb, (u32)j.n, (u32)j.dim, (u32)j.h, ex.st));
+                if (L.builder == Builder::Small) {
+                    KdSmallPlan sp = L.sp;
+                    const size_t gmax = (size_t)sp.occ * (size_t)cx->n_sms;
+                    sp.grid = (u32)(nb < gmax ? nb : gmax);
+                    CK(launch_kdsmall(sp, d_in + b0 * j.n * j.dim, region + b0 * L.region_stride, L.region_stride,
+                                      reinterpret_cast<u32 *>(ws), (u32)nb, (u32)j.n, (u32)j.dim, (u32)j.h, ex.st));
+                } else {   // clouds that stay in HBM (one shard of BASELINE cfg 5): the grid-wide build, piece by piece
+                    CK(launch_kd_gridbuild(d_in + b0 * j.n * j.dim, region + b0 * L.region_stride, L.region_stride, ws + L.aux_off,
+                                           (u32)nb, (u32)j.n, (u32)j.dim, (u32)j.h, ex.st));
+                }
             }
             // page-locked output (what the python module hands out): the sampler writes its 32-pick blocks straight into
             // host memory over PCIe while it runs, no device-to-host copy afterwards
@@ -855,14 +861,22 @@ static int shard_enqueue(DevCtx *cx, const ShardJob &j, cudaStream_t producer) {
                                         reinterpret_cast<u32 *>(ws + L.counter_off), (u32)j.B, (u32)j.n, (u32)j.dim, (u32)j.k, (u32)j.h,
                                         false, ex.st));
             if (!zero_copy && !j.keep_dev) CK(cudaMemcpyAsync(j.out, cp.out.p, j.B * out_per, cudaMemcpyDeviceToHost, ex.st));
-            set_plan("pipelined upload (%zu pieces) + kdsmall_kernel<DIM=%d> per piece + %s clouds=%zu%s",
-                     c, L.sp.dimp, L.sampler == Sampler::WarpOnChip ? "kdline_warp_kernel" : "kdline_stream_kernel", j.B,
-                     zero_copy ? " + indices written straight to page-locked host memory" : "");
+            char bd[48];
+            if (L.builder == Builder::Small) snprintf(bd, sizeof bd, "kdsmall_kernel<DIM=%d>", L.sp.dimp);
+            else snprintf(bd, sizeof bd, "gb_* grid-wide build");
+            if (L.sampler == Sampler::WarpOnChip)
+                set_plan("pipelined upload (%zu pieces) + %s per piece + kdline_warp_kernel clouds=%zu%s", c, bd, j.B,
+                         zero_copy ? " + indices written straight to page-locked host memory" : "");
+            else
+                set_plan("pipelined upload (%zu pieces) + %s per piece + kdline_stream_kernel<DIM=%d>: %s; clouds=%zu%s", c, bd, L.stp.dimp,
+                         L.stp.desc, j.B, zero_copy ? " + indices written straight to page-locked host memory" : "");
             return FPS_OK;
         }
     }
-    for (size_t c = 0, b0 = 0; b0 < j.B; ++c, b0 += chunk) {
-        const size_t nb = (j.B - b0 < chunk) ? j.B - b0 : chunk;
+    // the partial chunk goes FIRST: nothing hides the first upload, so it should be the small one (and for the streaming sampler
+    // the partial wave then runs on its wide teams while the next full chunk is crossing PCIe)
+    const size_t nchunks = (j.B + chunk - 1) / chunk, first = j.B - (nchunks - 1) * chunk;
+    for (size_t c = 0, b0 = 0, nb = first; b0 < j.B; ++c, b0 += nb, nb = chunk) {
         Lane &ln = cx->lane[c & 1];
         size_t ws_need;
         if (j.algo == FPS_ALGO_NPDU) {

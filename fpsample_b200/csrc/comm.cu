@@ -15,6 +15,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -48,13 +49,23 @@ struct NcclApi {
 };
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
+static char g_nccl_path[1024] = "";   // fps_b200_nccl_library
+static bool g_nccl_bound = false;
 
 static const NcclApi &nccl() {
     std::call_once(g_nccl_once, [] {
-        void *so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        // Which libnccl: (1) the one this process already has (a host framework such as PyTorch); (2) the one the host named
+        // (fps_b200_nccl_library / FPS_B200_NCCL_LIB -- the python package points at the pip-installed nvidia-nccl wheel, the
+        // copy PyTorch will load LATER if it is imported after us: two different libnccl.so.2 in one process do not work, the
+        // second user would be handed the first one's symbols); (3) the system's.
+        void *so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+        const char *named = g_nccl_path[0] ? g_nccl_path : getenv("FPS_B200_NCCL_LIB");
+        if (!so && named && named[0]) so = dlopen(named, RTLD_NOW | RTLD_GLOBAL);
+        if (!so) so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!so) so = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!so) return;
         g_nccl.so = so;
+        g_nccl_bound = true;
 #define BIND(field, sym) g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(so, sym))
         BIND(GetUniqueId, "ncclGetUniqueId");
         BIND(CommInitRank, "ncclCommInitRank");
@@ -328,6 +339,20 @@ void fps_b200_comm_destroy(void) {
 }
 
 int fps_b200_comm_ranks(void) { return g_nranks; }
+
+int fps_b200_nccl_library(const char *path) {
+    if (!path || strlen(path) >= sizeof g_nccl_path) {
+        comm_set_err("bad argument: need a path of fewer than %zu characters", sizeof g_nccl_path);
+        return FPS_ERR_ARG;
+    }
+    std::lock_guard<std::mutex> lk(g_comm_mu);
+    if (g_nccl_bound) {
+        comm_set_err("NCCL is already bound; name the library before the first comm call");
+        return FPS_ERR_NCCL;
+    }
+    snprintf(g_nccl_path, sizeof g_nccl_path, "%s", path);
+    return FPS_OK;
+}
 
 int fps_b200_nccl_version(void) {
     const NcclApi &N = nccl();

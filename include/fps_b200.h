@@ -125,6 +125,12 @@ FPS_API int fps_b200_comm_init_local(const int *devices, int n_devices);
 FPS_API void fps_b200_comm_destroy(void);
 FPS_API int fps_b200_comm_ranks(void);    /* 0 = no communicator */
 FPS_API int fps_b200_nccl_version(void);  /* e.g. 22809; 0 = NCCL not found */
+/* Optional, before the first comm call: the libnccl to bind when the process has not loaded one yet.  Search order: a
+ * libnccl.so.2 already in the process (a host framework's) -> this path (or the environment's FPS_B200_NCCL_LIB) ->
+ * the system's libnccl.so.2.  A process must not end up with two different libnccl.so.2: a host that will load its own
+ * copy LATER (PyTorch imported after the first comm call) names that copy here; the python package does so by itself
+ * (the pip-installed nvidia-nccl wheel).  FPS_ERR_NCCL if NCCL is already bound. */
+FPS_API int fps_b200_nccl_library(const char *path);
 /* Collective.  One process per GPU: `points` / `start` are THIS RANK's shard ([nb][n][dim], nb = its share of n_clouds; host or
  * device memory).  One process with several endpoints: the whole batch [n_clouds][n][dim] in host memory.  The indices of
  * all n_clouds clouds arrive in out_rank0 ([n_clouds][k], host memory) where rank 0 lives; other ranks pass NULL. */

@@ -101,6 +101,24 @@ def test_comm_entry_points_fail_loudly_without_a_communicator():
     assert e.value.rc == 7   # FPS_ERR_NCCL
 
 
+def test_binding_nccl_first_does_not_break_a_later_torch_import():
+    """The library binds NCCL at run time.  A process must never hold two different libnccl.so.2 (the second user is handed
+    the first one's symbols: `undefined symbol: ncclDevCommCreate` when the system's older NCCL was bound before PyTorch was
+    imported), so the python package names the pip-installed wheel PyTorch itself would load (fps_b200_nccl_library)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("from fpsample_b200 import capi\n"
+            "v = capi.nccl_version()\n"          # binds NCCL before torch is in the process
+            "import torch\n"
+            "t = torch.cuda.nccl.version() if hasattr(torch.cuda, 'nccl') else None\n"
+            "print(v, t, capi._bundled_nccl())\n")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    v, rest = r.stdout.split(None, 1)
+    if "None" not in rest.split()[-1]:   # there is a bundled wheel: the versions agree
+        assert int(v) > 0, r.stdout
+
+
 def _nccl_worker(rank, world, port, B, n, k, h, q):
     try:
         sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
