@@ -152,13 +152,12 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   /
 // merging the partial maxima into its own copy of the bucket maxima, the arg-max over them -- so no third exchange is needed
 // (checked with compute-sanitizer racecheck, profiles/r02_sanitizer_racecheck.log).
 template <int DIM, int WPC, int BPL>
-__device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 tm /* shared address */, u32 cnt_s) {
+__device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 lane, u32 tm /* shared address */, u32 cnt_s) {
     constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
     constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per max-point record
     constexpr u32 PE = PendEntry<DIM>::kBytes;     // bytes per pending-list entry
     constexpr u32 NW = WPC * BPL;                  // 32-bucket groups: flush-mask words, table slots per lane
     constexpr int G = 2;                           // 128-position chunks per block: 8 positions per lane in registers
-    const u32 lane = lane_id();
     const u32 npad = a.npad, dim = a.dim, S = a.S, k = a.k, R = a.R;
     unsigned char *rg = a.region + (size_t)cloud * a.region_stride;
     const float *q = reinterpret_cast<const float *>(rg);
@@ -525,7 +524,14 @@ __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 sched[S_THREADS / 32];
     __shared__ u64 cnt[8];   // executed work of this CTA (a.count)
-    const u32 warp = warp_id(), lane = lane_id();
+    // Left to itself the compiler re-reads the thread id (S2R, a 20-cycle scoreboard wait) and re-derives lane / team /
+    // warp-in-team wherever it needs them -- 11 % of the instructions of the 4-warp-team kernel.  Read through an opaque
+    // instruction it stays in ONE register; that register is only worth it where it does not turn into a spill (measured,
+    // sampling ms old -> new: 512 clouds x 3-D on 4-warp teams 29.5 -> 27.5; 1024 x 3-D on 2-warp teams 44.6 -> 45.0;
+    // 512 x 6-D 79.2 -> 84.0)
+    u32 tid = threadIdx.x;
+    if constexpr (WPC == 4 && DIM <= 4) asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const u32 warp = tid >> 5, lane = tid & 31u;
     const u32 team = warp / WPC, tw = warp % WPC;
     constexpr u32 teams = S_THREADS / 32 / WPC;
     if (threadIdx.x < 8) cnt[threadIdx.x] = 0;
@@ -534,7 +540,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs 
     // clouds are handed out dynamically
     u32 cloud = team * gridDim.x + blockIdx.x;
     while (cloud < a.B) {
-        stream_cloud<DIM, WPC, BPL>(a, cloud, team, tw, smem_u32(smem_raw) + team * a.team_bytes, smem_u32(cnt));
+        stream_cloud<DIM, WPC, BPL>(a, cloud, team, tw, lane, smem_u32(smem_raw) + team * a.team_bytes, smem_u32(cnt));
         if (tw == 0 && lane == 0) sched[team] = atomicAdd(a.counter, 1u) + teams * gridDim.x;
         team_sync<WPC>(team);
         cloud = sched[team];
