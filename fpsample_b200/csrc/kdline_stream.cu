@@ -101,7 +101,23 @@ __device__ __forceinline__ void sts32(u32 a, u32 v) { asm volatile("st.shared.u3
 __device__ __forceinline__ void sts128u(u32 a, u32 x, u32 y, u32 z, u32 w) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
-__device__ __forceinline__ float4 ldg128(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+// 128-bit loads under a per-lane predicate, as ONE predicated instruction each (an `if` around a load is a divergent branch
+// with its reconvergence bookkeeping and a second copy of the fill values): lanes whose predicate is off keep `fill`
+__device__ __forceinline__ float4 ldg128_if(const float *p, bool on, float fill) {   // read-only path (coordinates)
+    float4 v = make_float4(fill, fill, fill, fill);
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "l"(p), "r"((u32)on));
+    return v;
+}
+__device__ __forceinline__ float4 ldcg128_if(const float *p, bool on, float fill) {   // L2 only (distances: rewritten all the time)
+    float4 v = make_float4(fill, fill, fill, fill);
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
+                 : "+f"(v.x), "+f"(v.y), "+f"(v.z), "+f"(v.w)
+                 : "l"(p), "r"((u32)on)
+                 : "memory");
+    return v;
+}
 __device__ __forceinline__ float2 s_lds64(u32 a) {
     float2 f;
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(f.x), "=f"(f.y) : "r"(a));
@@ -151,7 +167,7 @@ __device__ __forceinline__ void l2_prefetch_bulk(const void *p, u32 bytes) {   /
 // after the passes (one partial maximum per warp and bucket).  Everything after that is done by every warp for itself --
 // merging the partial maxima into its own copy of the bucket maxima, the arg-max over them -- so no third exchange is needed
 // (checked with compute-sanitizer racecheck, profiles/r02_sanitizer_racecheck.log).
-template <int DIM, int WPC, int BPL>
+template <int DIM, int WPC, int BPL, bool EX>
 __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32 team, u32 tw, u32 lane, u32 tm /* shared address */, u32 cnt_s) {
     constexpr u32 SP = 32u * WPC * BPL;            // bucket slots of the team (>= S)
     constexpr u32 PRB = ((DIM + 3) / 4) * 16;      // bytes per max-point record
@@ -312,21 +328,17 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 for (u32 cb = my0; cb < my1; cb += G) {   // one block: G chunks of 128 positions, 4 per lane each
                     float4 x[DIM][G], old[G];
                     bool inside[G], edge = false;
+                    // one base address per block: component c of group g lies c * npad + g * 128 floats behind it
+                    const float *base = q + (size_t)(cb * 128 + lane * 4);
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
                         const u32 p4 = (cb + g) * 128 + lane * 4;
                         const bool any = cb + g < my1 && p4 < hi && p4 + 3 >= lo;
                         inside[g] = cb + g < my1 && p4 >= lo && p4 + 3 < hi;
                         edge = edge || (any && !inside[g]);
-                        old[g] = make_float4(-1.0f, -1.0f, -1.0f, -1.0f);   // never a maximum, never stored
+                        old[g] = ldcg128_if(base + (size_t)dim * npad + g * 128, any, -1.0f);   // -1: never a maximum, never stored
 #pragma unroll
-                        for (int c = 0; c < DIM; ++c) x[c][g] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (any) {
-                            old[g] = __ldcg(reinterpret_cast<const float4 *>(dis + p4));
-#pragma unroll
-                            for (int c = 0; c < DIM; ++c)
-                                if (c < (int)dim) x[c][g] = ldg128(q + (size_t)c * npad + p4);
-                        }
+                        for (int c = 0; c < DIM; ++c) x[c][g] = ldg128_if(base + (size_t)c * npad + g * 128, any && (EX || c < (int)dim), 0.0f);
                     }
                     if (__any_sync(FULL, edge)) {   // a run's first / last group: positions of the neighbour buckets drop out
 #pragma unroll
@@ -519,7 +531,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
 #undef S_OWNMAX
 }
 
-template <int DIM, int WPC, int BPL>
+template <int DIM, int WPC, int BPL, bool EX /* the cloud has exactly DIM dimensions: no per-component checks */>
 __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ u32 sched[S_THREADS / 32];
@@ -540,7 +552,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs 
     // clouds are handed out dynamically
     u32 cloud = team * gridDim.x + blockIdx.x;
     while (cloud < a.B) {
-        stream_cloud<DIM, WPC, BPL>(a, cloud, team, tw, lane, smem_u32(smem_raw) + team * a.team_bytes, smem_u32(cnt));
+        stream_cloud<DIM, WPC, BPL, EX>(a, cloud, team, tw, lane, smem_u32(smem_raw) + team * a.team_bytes, smem_u32(cnt));
         if (tw == 0 && lane == 0) sched[team] = atomicAdd(a.counter, 1u) + teams * gridDim.x;
         team_sync<WPC>(team);
         cloud = sched[team];
@@ -651,9 +663,9 @@ bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, Str
     return pl->nseg > 0;
 }
 
-template <int DIM, int WPC, int BPL>
+template <int DIM, int WPC, int BPL, bool EX>
 static cudaError_t launch_stream_t(const StreamSeg &pl, const StreamArgs &a, cudaStream_t st) {
-    auto kern = kdline_stream_kernel<DIM, WPC, BPL>;
+    auto kern = kdline_stream_kernel<DIM, WPC, BPL, EX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) return e;
     kern<<<pl.grid, S_THREADS, pl.smem, st>>>(a);
@@ -662,11 +674,18 @@ static cudaError_t launch_stream_t(const StreamSeg &pl, const StreamArgs &a, cud
 
 template <int DIM>
 static cudaError_t launch_stream_d(const StreamSeg &pl, const StreamArgs &a, cudaStream_t st) {
-    if (pl.wpc == 1) return launch_stream_t<DIM, 1, 4>(pl, a, st);
-    if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2>(pl, a, st);
-    if (pl.bpl == 1) return launch_stream_t<DIM, 4, 1>(pl, a, st);
-    if (pl.bpl == 2) return launch_stream_t<DIM, 4, 2>(pl, a, st);
-    return launch_stream_t<DIM, 4, 4>(pl, a, st);
+    // the exact-dimension kernels exist for the shapes of BASELINE.json's configs[4] (3 and 6 dimensions, teams of 2 / 4 warps)
+    if constexpr (DIM == 3 || DIM == 6) {
+        if (a.dim == (u32)DIM) {
+            if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2, true>(pl, a, st);
+            if (pl.wpc == 4 && pl.bpl == 1) return launch_stream_t<DIM, 4, 1, true>(pl, a, st);
+        }
+    }
+    if (pl.wpc == 1) return launch_stream_t<DIM, 1, 4, false>(pl, a, st);
+    if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2, false>(pl, a, st);
+    if (pl.bpl == 1) return launch_stream_t<DIM, 4, 1, false>(pl, a, st);
+    if (pl.bpl == 2) return launch_stream_t<DIM, 4, 2, false>(pl, a, st);
+    return launch_stream_t<DIM, 4, 4, false>(pl, a, st);
 }
 
 cudaError_t stream_debug_counters(u64 *out16) { return cudaMemcpyFromSymbol(out16, g_stream_wexec, sizeof(u64) * 16); }
