@@ -110,6 +110,14 @@ __device__ __forceinline__ float4 ldg128_if(const float *p, bool on, float fill)
                  : "l"(p), "r"((u32)on));
     return v;
 }
+__device__ __forceinline__ void stcg128_if(float *p, const float4 &v, bool on) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p st.global.cg.v4.f32 [%4], {%0, %1, %2, %3};\n}" ::"f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w), "l"(p), "r"((u32)on)
+                 : "memory");
+}
+__device__ __forceinline__ void stcg32_if(float *p, float v, bool on) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %2, 0;\n @p st.global.cg.f32 [%1], %0;\n}" ::"f"(v), "l"(p), "r"((u32)on) : "memory");
+}
 __device__ __forceinline__ float4 ldcg128_if(const float *p, bool on, float fill) {   // L2 only (distances: rewritten all the time)
     float4 v = make_float4(fill, fill, fill, fill);
     asm volatile("{\n .reg .pred p;\n setp.ne.u32 p, %5, 0;\n @p ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];\n}"
@@ -340,7 +348,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
 #pragma unroll
                         for (int c = 0; c < DIM; ++c) x[c][g] = ldg128_if(base + (size_t)c * npad + g * 128, any && (EX || c < (int)dim), 0.0f);
                     }
-                    if (__any_sync(FULL, edge)) {   // a run's first / last group: positions of the neighbour buckets drop out
+                    const bool hasedge = __any_sync(FULL, edge);
+                    if (hasedge) {   // a run's first / last group: positions of the neighbour buckets drop out
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
                             const u32 p4 = (cb + g) * 128 + lane * 4;
@@ -357,6 +366,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     const u32 e0 = pend + b * PE, estep = SP * PE;
                     float4 n0, n1;
                     PendEntry<DIM>::load(e0, n0, n1);
+                    // (not unrolled: the compiler's 4-way unrolling with its entry paths costs 3-5 % -- measured)
+#pragma unroll 1
                     for (u32 i = 0; i < nref; ++i) {
                         const float4 f0v = n0, f1v = n1;
                         PendEntry<DIM>::load(e0 + min(i + 1, nref - 1) * estep, n0, n1);
@@ -388,15 +399,16 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                             const u32 tot = __reduce_add_sync(FULL, nst);
                             if (lane == 0 && tot) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 56)), (u64)tot);
                         }
-                        if (ch) {
-                            if (inside[g]) {
-                                __stcg(reinterpret_cast<float4 *>(dis + p4), v[g]);
-                            } else {   // never touch a neighbour bucket's positions: another warp may be writing them
-                                if (v[g].x != old[g].x) __stcg(dis + p4 + 0, v[g].x);
-                                if (v[g].y != old[g].y) __stcg(dis + p4 + 1, v[g].y);
-                                if (v[g].z != old[g].z) __stcg(dis + p4 + 2, v[g].z);
-                                if (v[g].w != old[g].w) __stcg(dis + p4 + 3, v[g].w);
-                            }
+                        // only distances that changed go back, as one predicated store per group; at a run's ends single values:
+                        // never touch a neighbour bucket's positions, another warp may be writing them
+                        float *pd = const_cast<float *>(base) + (size_t)dim * npad + g * 128;
+                        stcg128_if(pd, v[g], ch && inside[g]);
+                        if (hasedge) {
+                            const bool e = ch && !inside[g];
+                            stcg32_if(pd + 0, v[g].x, e && v[g].x != old[g].x);
+                            stcg32_if(pd + 1, v[g].y, e && v[g].y != old[g].y);
+                            stcg32_if(pd + 2, v[g].z, e && v[g].z != old[g].z);
+                            stcg32_if(pd + 3, v[g].w, e && v[g].w != old[g].w);
                         }
                         // ascending positions: a lane keeps its first maximum
 #define S_TRACK(E, OFF)                                              \
