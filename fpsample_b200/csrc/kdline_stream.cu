@@ -190,12 +190,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     // team shared memory (32-bit shared addresses).  Everything whose size is known at compile time comes FIRST, so that its
     // address is `tm` + an immediate (no address arithmetic, no registers); the pending lists, whose depth R is a run-time
     // choice of the planner, come last:
-    // bucket records [SP] {lo, hi, pending, -} | max-point coordinates [SP] | fmask[NW] | flist[SP] (flushed buckets, compacted
+    // bucket records [SP] {lo, hi, pending, -} | max-point coordinates [SP] | fcnt[2] (+pad) | flist[SP] (flushed buckets, compacted
     // per group) | part[2][S_MAXF][WPC] | fslot[WPC] | pending lists [R][SP]
     const u32 brec = tm;
     const u32 bmcs = brec + SP * 16;
-    const u32 fmask = bmcs + SP * PRB;
-    const u32 flist = fmask + ((NW + 3) & ~3u) * 4;
+    const u32 fcnt = bmcs + SP * PRB;   // two counters (pick parity)
+    const u32 flist = fcnt + ((NW + 3) & ~3u) * 4;
     const u32 part = flist + SP * 4;
     const u32 fslot = part + 2 * S_MAXF * WPC * S_REC + tw * PRB;   // one per warp
     const u32 pend = part + 2 * S_MAXF * WPC * S_REC + WPC * PRB;
@@ -219,6 +219,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     float tmax[NW];
     u32 tpos[NW], tvalid = 0;
 #define S_OWNMAX(j) (*(WPC == 1 ? &tmax[(j)] : &bmax_[WPC == 1 ? 0 : (j)]))
+    if (tw == 0 && lane == 0) sts32(fcnt, 0u), sts32(fcnt + 4, 0u);
     team_sync<WPC>(team);
     {
         const float *fbox = reinterpret_cast<const float *>(rg) + (size_t)(dim + 2) * npad + a.nlo_pad;
@@ -273,9 +274,10 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 sts32(brec + b * 16 + 8, np[j]);
             }
             const bool flush = want && (hitmax || np[j] >= R);
-            const u32 m = __ballot_sync(FULL, flush);
-            if (flush) {   // into the group's compacted list; the bucket's lines start moving from HBM to L2 right away
-                sts32(flist + (grp * 32 + __popc(m & ((1u << lane) - 1u))) * 4, b);
+            if (flush) {   // into the team's list (any order will do: a pick's passes are independent of each other); the bucket's
+                           // lines start moving from HBM to L2 right away
+                const u32 slot = atomicAdd(reinterpret_cast<u32 *>(__cvta_shared_to_generic(fcnt + (t & 1u) * 4)), 1u);
+                sts32(flist + slot * 4, b);
                 if (a.prefetch) {
                     const uint4 br = lds128u(brec + b * 16);
                     const u32 p0 = br.x & ~3u, bytes = (((br.y + 3u) & ~3u) - p0) * 4u;
@@ -285,7 +287,6 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                         if (c < (int)dim) l2_prefetch_bulk(q + (size_t)c * npad + p0, bytes);
                 }
             }
-            if (lane == 0) sts32(fmask + grp * 4, m);
             if (a.count) {
                 const u32 ne = __popc(__ballot_sync(FULL, flush && !hitmax));
                 if (lane == 0 && ne) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 24)), (u64)ne);
@@ -296,27 +297,15 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         // ---- 2. bucket passes: every flushed bucket, this warp's run of chunks, all pending samples applied -----------------
         u32 fm = 0, fq = S_NONE;   // the best maximum among the buckets passed over in THIS pick (value bits, position); its
                                    // point is parked in this WARP's own slot: if it wins the arg-max, the coordinates come from there
-        u32 pre[NW];   // flushed buckets up to and including group w
-        {
-            u32 acc = 0;
-#pragma unroll
-            for (u32 w = 0; w < NW; ++w) {
-                acc += __popc(lds32(fmask + w * 4));
-                pre[w] = acc;
-            }
-        }
-        const u32 total = pre[NW - 1];
+        const u32 total = lds32(fcnt + (t & 1u) * 4);                  // flushed buckets of this pick
+        if (tw == 0 && lane == 0) sts32(fcnt + ((t + 1u) & 1u) * 4, 0u);   // the other counter: next pick's tests come after the next barrier
         for (u32 f0 = 0; f0 < total; f0 += S_MAXF) {   // batches of at most S_MAXF buckets between two exchanges
             const u32 nf = min(total - f0, S_MAXF);
             u32 myb = S_NONE;                         // lane fi remembers the bucket of flush slot fi
             const u32 pbuf = part + bp * (S_MAXF * WPC * S_REC);
             for (u32 fi = 0; fi < nf; ++fi) {
                 const u32 f = f0 + fi;
-                u32 w = 0, base = 0;                   // group of the f-th flushed bucket, flushed buckets before that group
-#pragma unroll
-                for (u32 x = 0; x + 1 < NW; ++x)
-                    if (f >= pre[x]) w = x + 1, base = pre[x];
-                const u32 b = lds32(flist + (w * 32 + (f - base)) * 4);
+                const u32 b = lds32(flist + f * 4);
                 if (lane == fi) myb = b;
                 const uint4 br = lds128u(brec + b * 16);
                 const u32 lo = br.x, hi = br.y, nref = br.z;
@@ -551,10 +540,10 @@ __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs 
     // Left to itself the compiler re-reads the thread id (S2R, a 20-cycle scoreboard wait) and re-derives lane / team /
     // warp-in-team wherever it needs them -- 11 % of the instructions of the 4-warp-team kernel.  Read through an opaque
     // instruction it stays in ONE register; that register is only worth it where it does not turn into a spill (measured,
-    // sampling ms old -> new: 512 clouds x 3-D on 4-warp teams 29.5 -> 27.5; 1024 x 3-D on 2-warp teams 44.6 -> 45.0;
-    // 512 x 6-D 79.2 -> 84.0)
+    // sampling ms without -> with: 512 clouds x 3-D on 4-warp teams 29.5 -> 27.5, 1024 x 3-D on 2-warp teams 39.2 -> 38.6,
+    // 512 x 6-D 73.7 -> 77.9)
     u32 tid = threadIdx.x;
-    if constexpr (WPC == 4 && DIM <= 4) asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    if constexpr (DIM <= 4) asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
     const u32 warp = tid >> 5, lane = tid & 31u;
     const u32 team = warp / WPC, tw = warp % WPC;
     constexpr u32 teams = S_THREADS / 32 / WPC;
