@@ -295,8 +295,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         team_sync<WPC>(team);
 
         // ---- 2. bucket passes: every flushed bucket, this warp's run of chunks, all pending samples applied -----------------
-        u32 fm = 0, fq = S_NONE;   // the best maximum among the buckets passed over in THIS pick (value bits, position); its
-                                   // point is parked in this WARP's own slot: if it wins the arg-max, the coordinates come from there
+        u64 fk = 0;                // the best maximum among the buckets passed over in THIS pick (as a record key) and its position; its
+        u32 fq = S_NONE;           // point is parked in this WARP's own slot: if it wins the arg-max, the coordinates come from there
         const u32 total = lds32(fcnt + (t & 1u) * 4);                  // flushed buckets of this pick
         if (tw == 0 && lane == 0) sts32(fcnt + ((t + 1u) & 1u) * 4, 0u);   // the other counter: next pick's tests come after the next barrier
         for (u32 f0 = 0; f0 < total; f0 += S_MAXF) {   // batches of at most S_MAXF buckets between two exchanges
@@ -418,10 +418,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 const u32 m = __reduce_max_sync(FULL, __float_as_uint(pv));
                 const u32 qpos = __reduce_min_sync(FULL, (__float_as_uint(pv) == m) ? bi : S_NONE);
                 const u32 rec = pbuf + (fi * WPC + tw) * S_REC;
+                // the record orders as ONE 64-bit key: (max bits, ~position) -- larger value first, then the lower position;
+                // "nothing" is the smallest key there is
                 if (qpos == S_NONE) {
-                    if (lane == 0) sts128u(rec, 0u, S_NONE, 0u, 0u);
+                    if (lane == 0) sts128u(rec, 0u, 0u, 0u, 0u);
                 } else if (bi == qpos) {   // positions are unique: exactly one lane
-                    sts128u(rec, m, qpos, 0u, 0u);
+                    sts128u(rec, m, ~qpos, 0u, 0u);
                     s_sts128(rec + 16, bc[0], DIM > 1 ? bc[DIM > 1 ? 1 : 0] : 0.f, DIM > 2 ? bc[DIM > 2 ? 2 : 0] : 0.f, DIM > 3 ? bc[DIM > 3 ? 3 : 0] : 0.f);
                     if constexpr (DIM > 4)
                         s_sts128(rec + 32, bc[4], DIM > 5 ? bc[DIM > 5 ? 5 : 0] : 0.f, DIM > 6 ? bc[DIM > 6 ? 6 : 0] : 0.f, DIM > 7 ? bc[DIM > 7 ? 7 : 0] : 0.f);
@@ -431,13 +433,16 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
             // ---- every warp merges the partial maxima into its own table: largest value, lowest position ------------------------
             for (u32 fi = 0; fi < nf; ++fi) {
                 const u32 b = __shfl_sync(FULL, myb, fi);
-                u32 m = 0, qpos = S_NONE, src = pbuf + (fi * WPC) * S_REC;
+                u64 bk = 0;
+                u32 src = pbuf + (fi * WPC) * S_REC;
 #pragma unroll
                 for (int w = 0; w < WPC; ++w) {
                     const u32 rec = pbuf + (fi * WPC + w) * S_REC;
                     const uint4 pr = lds128u(rec);
-                    if (pr.y != S_NONE && (qpos == S_NONE || pr.x > m || (pr.x == m && pr.y < qpos))) m = pr.x, qpos = pr.y, src = rec;
+                    const u64 key = (u64)pr.x << 32 | pr.y;
+                    if (key > bk) bk = key, src = rec;
                 }
+                const u32 m = (u32)(bk >> 32), qpos = ~(u32)bk;   // (nothing at all: qpos = S_NONE)
                 // (written as selects on purpose: an unrolled `if (slot == s) table[s] = ...` is turned into a dynamically indexed
                 // store by the compiler, which moves the whole table to local memory)
                 const bool mineb = (b & 31u) == lane;
@@ -447,8 +452,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     tmax[s] = hit ? __uint_as_float(m) : tmax[s];
                     tpos[s] = hit ? qpos : tpos[s];
                 }
-                if (qpos != S_NONE && (fq == S_NONE || m > fm || (m == fm && qpos < fq))) {   // (uniform over the warp)
-                    fm = m, fq = qpos;
+                if (bk > fk) {   // (uniform over the warp)
+                    fk = bk, fq = qpos;
                     if (lane == 0) {
                         const float4 c0v = s_lds128(src + 16);
                         s_sts128(fslot, c0v.x, c0v.y, c0v.z, c0v.w);
@@ -493,8 +498,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         const u32 M = __reduce_max_sync(FULL, kmax);
         const u32 mine = (cand != S_NONE && kmax == M) ? cand : S_NONE;
         cur = __reduce_min_sync(FULL, mine);
-        const u32 srcl = __ffs(__ballot_sync(FULL, mine == cur)) - 1;   // positions are unique: exactly one lane
-        const u32 bw = __shfl_sync(FULL, sb * 32 + lane, srcl);
+        const u32 bw = __reduce_max_sync(FULL, mine == cur ? sb * 32 + lane : 0u);   // positions are unique: exactly one lane
+                                                                                      // (redux 22 cycles; ballot + ffs + shfl ~90)
         {   // the winner's point: a bucket passed over in this pick -> this warp's own slot (written by lane 0 above); an older
             // maximum -> the table its owner filled before an earlier barrier
             __syncwarp();
