@@ -217,7 +217,8 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
     u32 np[BPL];
     // ---- every warp's own copy of ALL bucket maxima: lane l, slot s = bucket s * 32 + l ----------------------------------------
     float tmax[NW];
-    u32 tpos[NW], tvalid = 0;
+    u32 tposn[NW], tvalid = 0;   // tposn: the maximum's position, COMPLEMENTED: (max bits, ~position) orders as one 64-bit key, and
+                                 // an empty slot (0, 0) is the smallest key there is
 #define S_OWNMAX(j) (*(WPC == 1 ? &tmax[(j)] : &bmax_[WPC == 1 ? 0 : (j)]))
     if (tw == 0 && lane == 0) sts32(fcnt, 0u), sts32(fcnt + 4, 0u);
     team_sync<WPC>(team);
@@ -244,11 +245,12 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
             const u32 b = s * 32 + lane;
             const uint4 br = lds128u(brec + b * 16);
             tmax[s] = 0.0f;
-            tpos[s] = S_NONE;
+            tposn[s] = 0u;
             if (b < S && br.y > br.x) tvalid |= 1u << s;
         }
 #pragma unroll
-        for (int j = 0; j < BPL; ++j) S_OWNMAX(j) = FLT_MAX;   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103)
+        for (int j = 0; j < BPL; ++j)   // every bucket flushes on the first sample (KDNode::init, KDNode.h:84-103); empty slots stay 0
+            S_OWNMAX(j) = ((tvalid >> (tw * BPL + j)) & 1u) ? FLT_MAX : 0.0f;
     }
 
     u32 cur = a.starts ? (u32)a.starts[cloud] : 0u;   // POSITION in the permuted array (wrapper.hpp:54-55)
@@ -450,7 +452,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 for (u32 s = 0; s < NW; ++s) {
                     const bool hit = mineb && (b >> 5) == s;
                     tmax[s] = hit ? __uint_as_float(m) : tmax[s];
-                    tpos[s] = hit ? qpos : tpos[s];
+                    tposn[s] = hit ? (u32)bk : tposn[s];
                 }
                 if (bk > fk) {   // (uniform over the warp)
                     fk = bk, fq = qpos;
@@ -487,19 +489,20 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         }
 
         // ---- 3. arg-max over all buckets, by every warp for itself: largest max, lowest position (KDLineTree.h:56-67) ---------
-        u32 kmax = 0, cand = S_NONE, sb = 0;
+        u64 bestk = 0;
+        u32 sb = 0;
 #pragma unroll
         for (u32 s = 0; s < NW; ++s) {
-            if ((tvalid >> s) & 1u) {
-                const u32 kb = __float_as_uint(tmax[s]);
-                if (cand == S_NONE || kb > kmax || (kb == kmax && tpos[s] < cand)) kmax = kb, cand = tpos[s], sb = s;
-            }
+            const u64 key = (u64)__float_as_uint(tmax[s]) << 32 | tposn[s];
+            if (key > bestk) bestk = key, sb = s;
         }
+        const u32 kmax = (u32)(bestk >> 32);
         const u32 M = __reduce_max_sync(FULL, kmax);
-        const u32 mine = (cand != S_NONE && kmax == M) ? cand : S_NONE;
-        cur = __reduce_min_sync(FULL, mine);
-        const u32 bw = __reduce_max_sync(FULL, mine == cur ? sb * 32 + lane : 0u);   // positions are unique: exactly one lane
-                                                                                      // (redux 22 cycles; ballot + ffs + shfl ~90)
+        const u32 minen = kmax == M ? (u32)bestk : 0u;
+        const u32 curn = __reduce_max_sync(FULL, minen);   // the largest complement = the lowest position
+        cur = ~curn;
+        // positions are unique: exactly one lane holds the winner (redux 22 cycles; ballot + ffs + shfl ~90)
+        const u32 bw = __reduce_max_sync(FULL, (kmax == M && (u32)bestk == curn) ? sb * 32 + lane : 0u);
         {   // the winner's point: a bucket passed over in this pick -> this warp's own slot (written by lane 0 above); an older
             // maximum -> the table its owner filled before an earlier barrier
             __syncwarp();
