@@ -341,6 +341,8 @@ __device__ __forceinline__ void warp_cloud(const WarpArgs &a, const ST st, u32 c
                 const u32 e0 = pend + b * PRB, estep = S * PRB;
                 float4 n0 = lds128(e0), n1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if constexpr (DIM > 4) n1 = lds128(e0 + 16u);
+                // (kept rolled: the compiler's 2-way unrolling with its entry paths costs 1.7 % -- measured, 1.225 -> 1.204 ms on cfg 2)
+#pragma unroll 1
                 for (u32 i = 0; i < nref; ++i) {
                     const float4 f0 = n0;
                     [[maybe_unused]] const float4 f1 = n1;
