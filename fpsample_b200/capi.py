@@ -52,6 +52,7 @@ EXPORTS = {
     "fps_b200_phase_timing": (None, [ctypes.c_int]),
     "fps_b200_last_phase_ms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "fps_b200_sync_floor": (ctypes.c_int, [ctypes.c_int] * 4 + [ctypes.c_void_p]),
+    "fps_b200_describe_stream_plan": (ctypes.c_int, [ctypes.c_size_t] * 4 + [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
     "fps_b200_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "fps_b200_host_free": (None, [ctypes.c_void_p]),
 }
@@ -170,6 +171,13 @@ def sync_floor(kind: int, ctas: int = 1, words: int = 0, group: int = 0, rounds:
     ns = ctypes.c_float(0)
     _check("fps_b200_sync_floor", lib().fps_b200_sync_floor(kind, ctas, (group << 16) | words, rounds, ctypes.byref(ns)))
     return float(ns.value)
+
+
+def describe_stream_plan(n_clouds: int, n: int, dim: int, height: int, n_sms: int = 148) -> str:
+    """how the streaming sampler cuts a batch into launches (host arithmetic only: works without a GPU)"""
+    buf = ctypes.create_string_buffer(256)
+    _check("fps_b200_describe_stream_plan", lib().fps_b200_describe_stream_plan(n_clouds, n, dim, height, n_sms, buf, len(buf)))
+    return buf.value.decode()
 
 
 def device_count() -> int:

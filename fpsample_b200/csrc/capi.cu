@@ -1132,6 +1132,20 @@ int fps_b200_set_tuning(const char *name, long value) {
     return FPS_OK;
 }
 
+int fps_b200_describe_stream_plan(size_t n_clouds, size_t n, size_t dim, size_t height, int n_sms, char *buf, size_t buf_len) {
+    if (!buf || buf_len == 0 || n_sms <= 0) {
+        set_err("bad argument: need a buffer and a positive SM count");
+        return FPS_ERR_ARG;
+    }
+    StreamPlan pl;
+    if (!plan_kdline_stream(n, dim, height, n_clouds, n_sms, &pl)) {
+        set_err("the streaming sampler does not take %zu clouds of %zu x %zu points at height %zu", n_clouds, n, dim, height);
+        return FPS_ERR_UNSUPPORTED;
+    }
+    snprintf(buf, buf_len, "%s", pl.desc);
+    return FPS_OK;
+}
+
 void fps_b200_set_producer_stream(void *stream) { tl_producer = stream ? static_cast<cudaStream_t>(stream) : cudaStreamLegacy; }
 
 void fps_b200_phase_timing(int enable) { g_phase_timing.store(enable ? 1 : 0); }

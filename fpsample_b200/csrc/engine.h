@@ -123,7 +123,7 @@ struct StreamPlan {   // a batch is cut into at most three runs of clouds, narro
     int dimp;
     u32 nseg;
     StreamSeg seg[3];
-    char desc[160];   // "1184 clouds x 2 warps (R=11) + 16 clouds x 4 warps (R=16)"
+    char desc[256];   // "1184 clouds x WPC=2 (...) + 16 clouds x WPC=4 (...)"
 };
 bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, StreamPlan *pl);
 cudaError_t launch_kdline_stream(const StreamPlan &pl, unsigned char *region, size_t region_stride, const u64 *starts, u64 *out,

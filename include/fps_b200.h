@@ -217,6 +217,11 @@ FPS_API int fps_b200_last_phase_ms(float *build_ms, float *sample_ms);
 #define FPS_FLOOR_CLUSTER 1
 #define FPS_FLOOR_GRID 2
 FPS_API int fps_b200_sync_floor(int kind, int ctas, int words, int rounds, float *ns_per_round);
+/* How the streaming sampler (big batches of clouds that stay in HBM: BASELINE.json configs[4]) would cut a batch of
+ * `n_clouds` clouds on a GPU of `n_sms` SMs into launches: full waves of narrow teams of warps + a partial wave of wide
+ * ones, e.g. "3552 clouds x WPC=2 (...) + 544 clouds x WPC=4 (...)".  Pure host arithmetic (no device needed); honours
+ * the tuning knobs STREAM_WARPS / STREAM_SPLIT.  FPS_ERR_UNSUPPORTED if the shape is not one the sampler takes. */
+FPS_API int fps_b200_describe_stream_plan(size_t n_clouds, size_t n, size_t dim, size_t height, int n_sms, char *buf, size_t buf_len);
 FPS_API void *fps_b200_host_alloc(size_t bytes);    /* page-locked host memory for the host-pointer entries   */
 FPS_API void fps_b200_host_free(void *p);
 

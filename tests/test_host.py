@@ -184,3 +184,31 @@ def test_cuda_array_interface_is_validated_on_the_host():
         fps._cuda_view(Dev((100, 3)), 3)
     with pytest.raises(AssertionError):
         fps.bucket_fps_kdline_sampling_batch(Dev((2, 100, 3)), 200, 3)       # n_samples > n_pts, before any device call
+
+
+def test_streaming_sampler_wave_plan():
+    """plan_kdline_stream (host arithmetic, no device): a batch is cut into FULL waves of narrow teams of warps (8 two-warp
+    teams per SM) and a last partial wave on wide teams (4 four-warp teams per SM); wide records (> 4 dimensions) and more
+    than 128 buckets need four-warp teams; the knobs override."""
+    from fpsample_b200 import capi
+    P = lambda B, d=3, h=7, sms=148: capi.describe_stream_plan(B, 100000, d, h, sms)
+    assert P(512).startswith("512 clouds x WPC=4")                                   # one wave of four-warp teams (an 8-GPU shard of cfg 5)
+    assert P(700).startswith("700 clouds x WPC=2")                                   # more than 592: one wave of two-warp teams
+    assert P(1184).startswith("1184 clouds x WPC=2") and "+" not in P(1184)
+    assert P(1200).startswith("1184 clouds x WPC=2") and "+ 16 clouds x WPC=4" in P(1200)
+    assert P(4096).startswith("3552 clouds x WPC=2") and "+ 544 clouds x WPC=4" in P(4096)
+    assert "WPC=2" not in P(4096, d=6) and "4096 clouds x WPC=4" in P(4096, d=6)      # 24-byte pending entries
+    assert "WPC=2" not in P(4096, h=9) and "BPL=4" in P(4096, h=9)                   # 512 buckets: four per lane
+    half = P(2048, sms=74)                                                          # waves scale with the SM count
+    assert half.startswith("1776 clouds x WPC=2") and "+ 272 clouds x WPC=4" in half
+    for B in (1, 3, 591, 593, 1183, 1185, 2367, 2369, 5000, 100000):                # every cloud is in exactly one launch
+        parts = [int(x.split(" clouds")[0]) for x in P(B).split(" + ")]
+        assert sum(parts) == B, P(B)
+    with capi.tuning(stream_split=0):                                               # one team size per batch (the earlier plan)
+        assert P(4096).startswith("4096 clouds x WPC=2") and P(512).startswith("512 clouds x WPC=4")
+    with capi.tuning(stream_split=2):                                               # one-warp teams allowed: 16 per SM
+        assert P(4096).startswith("2368 clouds x WPC=1")
+    with capi.tuning(stream_warps=4):
+        assert P(4096).startswith("4096 clouds x WPC=4")
+    with pytest.raises(capi.FpsError):
+        capi.describe_stream_plan(10, 1000, 9, 5)                                   # kd-line: at most 8 dimensions
