@@ -289,7 +289,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                         if (c < (int)dim) l2_prefetch_bulk(q + (size_t)c * npad + p0, bytes);
                 }
             }
-            if (a.count) {
+            if (!EX && a.count) {
                 const u32 ne = __popc(__ballot_sync(FULL, flush && !hitmax));
                 if (lane == 0 && ne) atomicAdd(reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s + 24)), (u64)ne);
             }
@@ -313,7 +313,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                 const u32 lo = br.x, hi = br.y, nref = br.z;
                 const u32 c0 = lo >> 7, ncn = ((hi - 1) >> 7) - c0 + 1, per = (ncn + WPC - 1) / WPC;
                 const u32 my0 = c0 + tw * per, my1 = min(my0 + per, c0 + ncn);
-                if (a.count && tw == 0 && lane == 0) {
+                if (!EX && a.count && tw == 0 && lane == 0) {
                     u64 *cs = reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s));
                     atomicAdd(cs + 0, (u64)(hi - lo));
                     atomicAdd(cs + 1, (u64)(hi - lo) * nref);
@@ -384,7 +384,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
                     for (int g = 0; g < G; ++g) {
                         const u32 p4 = (cb + g) * 128 + lane * 4;
                         const bool ch = v[g].x != old[g].x || v[g].y != old[g].y || v[g].z != old[g].z || v[g].w != old[g].w;
-                        if (a.count) {   // distances written back: whole 16-byte groups inside the bucket, single values at its ends
+                        if (!EX && a.count) {   // distances written back: whole 16-byte groups inside the bucket, single values at its ends
                             const u32 nst = inside[g] ? (ch ? 4u : 0u)
                                                       : (u32)(v[g].x != old[g].x) + (u32)(v[g].y != old[g].y) + (u32)(v[g].z != old[g].z) + (u32)(v[g].w != old[g].w);
                             const u32 tot = __reduce_add_sync(FULL, nst);
@@ -530,7 +530,7 @@ __device__ __forceinline__ void stream_cloud(const StreamArgs &a, u32 cloud, u32
         const u32 k0 = (k - 1) & ~31u;   // tail: picks [k0, k)
         if (k0 + lane < k) out[k0 + lane] = (u64)__ldg(perm + mypos);
     }
-    if (a.count && lane == 0 && tw == 0) {
+    if (!EX && a.count && lane == 0 && tw == 0) {
         u64 *cs = reinterpret_cast<u64 *>(__cvta_shared_to_generic(cnt_s));
         atomicAdd(cs + 4, (u64)(k - 1) * S);   // bucket tests
         atomicAdd(cs + 5, (u64)(k - 1));       // picks
@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(S_THREADS, 1) kdline_stream_kernel(StreamArgs 
         team_sync<WPC>(team);
         cloud = sched[team];
     }
-    if (a.count) {
+    if (!EX && a.count) {
         __syncthreads();
         if (threadIdx.x < 8) atomicAdd(&g_stream_wexec[threadIdx.x], cnt[threadIdx.x]);
     }
@@ -685,7 +685,7 @@ template <int DIM>
 static cudaError_t launch_stream_d(const StreamSeg &pl, const StreamArgs &a, cudaStream_t st) {
     // the exact-dimension kernels exist for the shapes of BASELINE.json's configs[4] (3 and 6 dimensions, teams of 2 / 4 warps)
     if constexpr (DIM == 3 || DIM == 6) {
-        if (a.dim == (u32)DIM) {
+        if (a.dim == (u32)DIM && !a.count) {   // (the executed-work counters are compiled into the general kernels only)
             if (pl.wpc == 2) return launch_stream_t<DIM, 2, 2, true>(pl, a, st);
             if (pl.wpc == 4 && pl.bpl == 1) return launch_stream_t<DIM, 4, 1, true>(pl, a, st);
         }
