@@ -26,6 +26,17 @@
 // buckets to pass over) and after the bucket passes (per-warp partial maxima); merging those and the arg-max over all
 // buckets are done by every warp for itself.  A bucket that is going to be passed over is prefetched into L2 with one
 // cp.async.bulk.prefetch per component the moment its owner lane decides so, before the first barrier.
+//
+// Every warp of a team executes the whole pick loop, and a warp issues a dependent instruction every 4-5 cycles: the
+// cost of a pick is its instruction count.  What keeps that count down ("Why the streaming fraction ..."):
+//   * one base address per block and predicated 128-bit loads / stores (no divergent branch around memory accesses);
+//   * exact-dimension kernels (EX: the cloud has exactly DIM dimensions; no per-component checks, no counters);
+//   * the thread id read once through an opaque instruction (no S2R re-reads, no re-derived lane / team ids);
+//   * flushed buckets claim list slots with a shared-memory counter (no ballots, popc prefix counts or searches);
+//   * maxima travel as 64-bit keys (max bits, ~position): one compare per record, an empty slot is the smallest key;
+//   * cross-lane results through redux.sync (22 cycles) rather than ballot + find-first-set + shuffle (~90).
+// The host side cuts a batch into full waves of two-warp teams and a last, partial wave of four-warp teams
+// (plan_kdline_stream; fps_b200_describe_stream_plan shows the cut).
 #include <cfloat>
 
 #include <cstdio>
