@@ -14,6 +14,9 @@
 //              KDTreeBase.h:123-149: k-th misplaced from the left pairs with the k-th from the right)
 //   gb_swap    one warp per item: the swaps; child boundaries; child box reset
 //   gb_box     one warp per item: tight child boxes (KDTreeBase.h:181-207) by redux + atomics on ordered ints
+// The item kernels are memory-latency programs: whatever an item loads is loaded BEFORE its first store (gb_rank: the
+// item's column values; gb_swap: every row value of a batch of pairs) -- a store may alias a later load as far as the
+// compiler knows, so a load behind a store waits for it: one memory round trip per loop iteration otherwise.
 #include <algorithm>
 #include <cfloat>
 
