@@ -622,15 +622,16 @@ bool plan_kdline_stream(size_t n, size_t dim, size_t h, size_t B, int n_sms, Str
     const u32 S = 1u << h;
     const int dimp = stream_dim((int)dim);
     // Warps per cloud (measured, 100 k-point clouds x 3, 2^7 buckets, one B200).  A pick is a dependent chain whose length hardly
-    // depends on how many other teams share the SM: a cloud takes ~85 / 44 / 28 ms on a team of 1 / 2 / 4 warps whether the SM
-    // is full or not, and an SM holds 16 / 8 / 4 such teams.  So a batch wants FULL WAVES of narrow teams (most clouds per SM)
+    // depends on how many other teams share the SM: a cloud took ~85 / 44 / 28 ms on a team of 1 / 2 / 4 warps whether the SM
+    // was full or not when the plan was made (35 / 21 ms on 2 / 4 warps with the final kernel: the same ratio), and an SM
+    // holds 16 / 8 / 4 such teams.  So a batch wants FULL WAVES of narrow teams (most clouds per SM)
     // and a last, partial wave of wide teams (short chain) instead of a half-empty wave of narrow ones: 4096 clouds =
     // 3 x 1184 on two warps + 544 on four, not 3.46 waves of two-warp teams.  The cut is a small dynamic programme over the
     // remaining clouds in units of one wave of the widest team.  One-warp teams only have room for 4 pending samples per
     // bucket (+18 % DRAM traffic) and are opt-in (STREAM_SPLIT=2); records of more than 4 dimensions and more than 128
     // buckets need the shared memory / lanes of a 4-warp team.
     const u32 widths[3] = {1, 2, 4};
-    const double cost[3] = {85.0, 44.0, 28.0};
+    const double cost[3] = {85.0, 44.0, 28.0};   // relative time of one wave per team size
     StreamSeg cand[3];
     bool ok[3];
     for (int i = 0; i < 3; ++i) ok[i] = stream_seg(dimp, S, widths[i], 1, n_sms, &cand[i]);
